@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the gnngls hot path on B200:  TSP100 regret_pred + GLS instances/sec.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (hand-written sm_100a CUDA)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference path
+
+A step = one pass of the hot path (features -> EdgePropertyPredictionModel -> inverse-scale/clamp ->
+nearest_neighbor -> tour_cost -> guided_local_search with a fixed number of outer iterations) over
+this rank's shard of synthetic instances.  Instances shard across ranks with no collective on the
+data path; the final gather of tours/costs over NCCL is inside the timed region.  One JSON line is
+printed by rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'TSP100 regret_pred+GLS instances/sec'
+UNIT = 'instances/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--n', type=int, default=100, help='cities per instance')
+    ap.add_argument('--instances-per-gpu', type=int, default=4096)
+    ap.add_argument('--gls-iters', type=int, default=10, help='GLS outer iterations K (fixed count, SURVEY 8(d))')
+    ap.add_argument('--perturbation-moves', type=int, default=20)
+    ap.add_argument('--micro-batch', type=int, default=32)
+    ap.add_argument('--chunk', type=int, default=1024, help='instances per host->device chunk in the e2e path')
+    ap.add_argument('--cpu-sample', type=int, default=4, help='instances in the bounded CPU-baseline sample')
+    ap.add_argument('--ref-sample', type=int, default=2, help='instances per step of the reference arm')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def make_port_model():
+    """Random-init weights in the reference checkpoint layout (LFS payloads are absent), seed 0."""
+    from oracle import model_port
+    torch.manual_seed(0)
+    return model_port.EdgeModelPort(1, 128, 1, 3, n_heads=8).eval()
+
+
+def make_model(device):
+    from gnngls_b200 import models
+    torch.manual_seed(0)
+    m = models.EdgePropertyPredictionModel(1, 128, 1, 3, n_heads=8)      # shipped params.json shape
+    ck = os.path.join(ROOT, 'models', 'tsp100', 'checkpoint_best_val.pt')
+    src = 'random-init(seed 0)'
+    if os.path.exists(ck) and os.path.getsize(ck) > 1 << 20:
+        m.load_state_dict(torch.load(ck, map_location='cpu')['model_state_dict'])
+        src = ck
+    return m.to(device).eval(), src
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_pass(port, D, n_iters, pm, threads):
+    """The reference's test.py:72-95 flow on CPU via the oracle: torch-CPU model (all threads) then the
+    C port of nearest_neighbor + guided_local_search across `threads` host threads."""
+    from gnngls_b200 import instances
+    from gnngls_b200.pipeline import Scalers
+    from oracle import gls_port, model_port
+    s = Scalers()
+    B, n = D.shape[0], D.shape[-1]
+    N = n * (n - 1) // 2
+    x = instances.edge_features(D)
+    x = ((x.astype(np.float64) * s.feat_scale).astype(np.float32).astype(np.float64) + s.feat_min).astype(np.float32)
+    g = model_port.EdgeListGraph.kn_line_graph(n, 1)
+    regret = np.empty((B, N), dtype=np.float32)
+    with torch.no_grad():
+        for b in range(B):                                      # one instance at a time, like test.py:59
+            y = port(g, torch.from_numpy(x[b]).reshape(-1, 1)).numpy().reshape(-1)
+            r = ((y.astype(np.float64) - s.regret_min).astype(np.float32).astype(np.float64) / s.regret_scale).astype(np.float32)
+            regret[b] = np.maximum(r, 0)
+    return gls_port.pipeline_batch(D, regret, n_iters, pm, nthreads=threads)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from gnngls_b200 import instances
+    from oracle import gls_port
+    gls_port.build()
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    port = make_port_model()
+    _, D = instances.random_instances(args.ref_sample, args.n)
+    for _ in range(args.warmup):
+        cpu_reference_pass(port, D, args.gls_iters, args.perturbation_moves, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_pass(port, D, args.gls_iters, args.perturbation_moves, threads)
+    dt = time.perf_counter() - t0
+    value = args.ref_sample * args.steps / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'fp32 (model) / fp64 (search)', 'data': 'synthetic',
+        'config': workload_config(args, world),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': f'{args.ref_sample} TSP{args.n} instances per step: oracle torch-CPU model (restated '
+                                   f'GATConv, {threads} threads) + C port of nearest_neighbor/GLS, K={args.gls_iters}'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        'workload': f'TSP{args.n}: EdgePropertyPredictionModel(1,128,1,3,n_heads=8) regret_pred + nearest_neighbor + '
+                    f'guided_local_search(guides=[regret_pred], perturbation_moves={args.perturbation_moves}, '
+                    f'K={args.gls_iters} fixed outer iterations)',
+        'n': args.n, 'instances_per_gpu': args.instances_per_gpu, 'global_instances': args.instances_per_gpu * world,
+        'gls_outer_iters': args.gls_iters, 'perturbation_moves': args.perturbation_moves,
+        'micro_batch': args.micro_batch, 'parallelism': f'instance-sharded x{world}, final NCCL gather only',
+        'l2': 'per-step inputs+activations exceed the 126 MB L2 (no explicit flush)',
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    import torch.distributed as dist
+    from gnngls_b200 import _lib, _timing, instances, pipeline
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; gnngls_b200 has no CPU path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    model, weights = make_model(dev)
+    solver = pipeline.RegretGLS(model, micro_batch=args.micro_batch)
+    S, n = args.instances_per_gpu, args.n
+    _, D_np = instances.random_instances(S, n, seed=instances.DEFAULT_SEED + rank)
+    D_host = torch.from_numpy(D_np).pin_memory()
+    D_dev = D_host.to(dev)
+    kw = dict(n_iters=args.gls_iters, perturbation_moves=args.perturbation_moves)
+    g_tours = torch.empty(world * S, n + 1, dtype=torch.int32, device=dev) if world > 1 else None
+    g_costs = torch.empty(world * S, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step_resident():
+        res = solver.solve(D_dev, **kw)
+        if world > 1:       # the only collective: final result gather over NCCL/NVLink
+            dist.all_gather_into_tensor(g_tours, res.best_tours)
+            dist.all_gather_into_tensor(g_costs, res.best_costs)
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        res = step_resident()
+    barrier()
+    # ---------------- timed region: inputs resident in HBM
+    launches0 = lib.launches
+    timer = _timing.StageTimer()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks, timer:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            res = step_resident()
+        ev1.record()
+        barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    launches = lib.launches - launches0
+    value = world * S * args.steps / (ms / 1e3)
+    stages = timer.totals_ms()
+    counters = res.counters.sum(0).tolist()        # last step: sweeps / o2a scans / moves on this rank
+
+    # ---------------- e2e: public API on HOST buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        solver.solve_host(D_host[: min(S, args.chunk)], chunk=args.chunk, **kw)          # warm pinned staging
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            tours_h, costs_h = solver.solve_host(D_host, chunk=args.chunk, **kw)
+        t1.record()
+        barrier()
+        ms2 = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * S * args.steps / (float(ms2) / 1e3), 'unit': UNIT,
+               'h2d_bytes_per_step': int(D_host.numel() * 8), 'd2h_bytes_per_step': int(S * (n + 1) * 4 + S * 8),
+               'api': 'gnngls_b200.pipeline.RegretGLS.solve_host (pinned host D -> tours/costs on host)'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel: the GAT aggregate (K_n star + combine)
+    N_nodes, E = n * (n - 1) // 2, n * (n - 1) * (n - 2)
+    gat_ms, gat_calls = stages.get('gat_kn', stages.get('gat_csr', (0.0, 0)))
+    per_call_instances = min(args.micro_batch, S)
+    alg_bytes_per_instance_layer = E * 544 + N_nodes * 544            # 544 B/edge + 544 B/node
+    peak, peak_src = peaks()
+    roof = None
+    if gat_calls:
+        # every timed call covers <= micro_batch instances; total instance-layers = steps * S * 8
+        total_bytes = alg_bytes_per_instance_layer * S * 8 * args.steps
+        achieved = total_bytes / (gat_ms / 1e3) / 1e9
+        roof = {'kernel': 'gat_kn_star_kernel + gat_kn_combine_kernel (one aggregate launch pair per layer)',
+                'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': alg_bytes_per_instance_layer * per_call_instances,
+                'avg_launch_ms': gat_ms / gat_calls, 'launches_timed': gat_calls,
+                'note': 'algorithmic gather bytes (544 B/edge); the star kernel serves them from shared memory after '
+                        'reading each ft row twice, so frac > 1 is reuse, not skipped work (see DESIGN.md)'}
+    total_stage = sum(v[0] for v in stages.values())
+    stage_ms = {k: round(v[0] / args.steps, 3) for k, v in stages.items()}
+    cand_2opt, cand_rel = (n - 2) * (n - 3) // 2, (n - 2) ** 2
+    gls_ms = stages.get('gls', (0.0, 0))[0] / max(args.steps, 1)
+    moves = {'a2a_candidates_per_s': (counters[0] * cand_2opt + counters[1] * cand_rel) / (gls_ms / 1e3) if gls_ms else None,
+             'two_opt_sweeps': counters[0], 'relocate_sweeps': counters[1], 'o2a_scans': counters[2],
+             'accepted_moves': counters[3], 'note': 'per step on rank 0; rate = a2a candidates / GLS kernel time'}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import gls_port
+        gls_port.build()
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        port = make_port_model()
+        sample = min(args.cpu_sample, S)
+        t0 = time.perf_counter()
+        o_t, o_c = cpu_reference_pass(port, D_np[:sample], args.gls_iters, args.perturbation_moves, threads)
+        dt = time.perf_counter() - t0
+        cpu = {'value': sample / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+               'sample': f'first {sample} instances of the same workload, {dt:.1f} s: oracle torch-CPU model + C port '
+                         f'of nearest_neighbor/GLS (K={args.gls_iters})',
+               'best_cost_mean_cpu': float(o_c.mean()),
+               'best_cost_mean_gpu_same_instances': float(res.best_costs[:sample].mean())}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'tf32 (GNN contractions, fp32 accumulate) + fp64 (search)', 'data': 'synthetic',
+        'config': dict(workload_config(args, world), weights=weights),
+        'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu,
+        'stage_ms_per_step': stage_ms, 'stage_coverage': round(total_stage / ms, 3) if ms else None,
+        'search': moves, 'mean_best_cost': float(res.best_costs.mean()), 'mean_init_cost': float(res.init_costs.mean()),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

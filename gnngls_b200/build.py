@@ -1,0 +1,79 @@
+"""Builds libgnngls_b200.so (hand-written sm_100a CUDA + the C ABI) in-tree with nvcc.
+
+    python -m gnngls_b200.build [--force]
+
+nvcc cross-compiles for sm_100a without a GPU.  The library is linked against the static CUDA
+runtime so it only needs the driver at run time.
+"""
+import concurrent.futures
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
+OUT_DIR = os.path.join(HERE, '_lib')
+LIB_PATH = os.path.join(OUT_DIR, 'libgnngls_b200.so')
+
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-I', INCLUDE, '-I', CSRC]
+# per-translation-unit extra flags; the search/glue units must never contract a*b+c into an FMA
+SOURCES = {
+    'common.cu': [],
+    'search.cu': ['-fmad=false'],
+    'glue.cu': ['-fmad=false'],
+    'gat.cu': [],
+    'dense.cu': [],
+}
+
+
+def nvcc():
+    path = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(path):
+        raise RuntimeError('nvcc not found; cannot build libgnngls_b200.so')
+    return path
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OUT_DIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
+    headers += [os.path.join(INCLUDE, 'gnngls_b200.h'), os.path.abspath(__file__)]
+    jobs, objs = [], []
+    for src, extra in SOURCES.items():
+        sp = os.path.join(CSRC, src)
+        if not os.path.exists(sp):
+            raise RuntimeError('missing source ' + sp)
+        obj = os.path.join(OUT_DIR, src.replace('.cu', '.o'))
+        objs.append(obj)
+        if force or _stale(obj, [sp] + headers):
+            jobs.append([nvcc()] + ARCH + COMMON + extra + ['-c', sp, '-o', obj])
+
+    def run(cmd):
+        if verbose:
+            print(' '.join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + r.stdout + r.stderr)
+        return r.stderr
+
+    if jobs:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            for warn in ex.map(run, jobs):
+                if verbose and warn.strip():
+                    print(warn)
+    if force or jobs or _stale(LIB_PATH, objs):
+        run([nvcc()] + ARCH + ['-shared', '-o', LIB_PATH] + objs)
+    return LIB_PATH
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose=True))

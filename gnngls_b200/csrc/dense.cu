@@ -1,0 +1,516 @@
+// Dense contractions of the edge-regret model on sm_100a.
+//
+//   fc   : ft = h Wfc^T (+ attention scores el/er in the epilogue)      GATConv.fc, models.py:23
+//   ff1  : hid = relu(h1 W1^T + b1)                                      models.py:30-31
+//   ff2  : h   = BN2(h1 + hid W2^T + b2)                                 models.py:32-35
+//
+// Main path: one persistent, warp-specialised kernel template — TMA (cp.async.bulk.tensor, 128B
+// swizzle) feeds a 6-stage shared-memory ring, a single thread issues tcgen05.mma kind::tf32 with
+// fp32 accumulators in TMEM (double-buffered, 2 x 128 columns), four epilogue warps drain TMEM with
+// tcgen05.ld, transpose through shared memory and apply the fused epilogue with coalesced 128-bit
+// global accesses.  Operands are fp32 in memory; activations written by these epilogues are
+// rounded to TF32 (cvt.rna) so that the tensor core's operand truncation is exact.
+//
+// Debug path (GNNGLS_DENSE_SIMT): plain fp32 CUDA-core GEMM with the same epilogues, used by the
+// tests to cross-check the tensor-core path.  Also here: embed_layer and decision_layer, which
+// are K=in_dim / N=out_dim degenerate and run as fused elementwise / dot-product kernels.
+#include <cuda.h>
+#include <cstdint>
+#include "common.h"
+
+namespace {
+
+constexpr int D_ = GNNGLS_EMBED_DIM;     // 128
+constexpr int H_ = GNNGLS_HEADS;         // 8
+constexpr int HID_ = GNNGLS_HIDDEN_DIM;  // 512
+
+enum { EPI_FC = 0, EPI_FF1 = 1, EPI_FF2 = 2 };
+
+struct EpiParams {
+    int64_t M;
+    float *out;          // FC: ft [M,128]; FF1: hid [M,512]; FF2: h_out [M,128]
+    float *el, *er;      // FC only, [M,8]
+    const float *v0;     // FC: attn_l[128]; FF1: b1[512]; FF2: b2[128]
+    const float *v1;     // FC: attn_r[128]; FF2: bn_scale[128]
+    const float *v2;     // FF2: bn_shift[128]
+    const float *skip;   // FF2: h1 [M,128]
+    int round_tf32;      // round stored activations to TF32 (tensor-core path)
+};
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// Fused epilogue for 4 consecutive columns [col, col+4) of one row.  Called with a full warp in
+// which lanes 4q..4q+3 hold consecutive column quads of the same row (needed by the FC reduction).
+template <int EPI>
+__device__ __forceinline__ void epilogue_quad(const EpiParams &p, int64_t row, int col, float4 acc, bool valid) {
+    if (EPI == EPI_FC) {
+        const float4 al = *reinterpret_cast<const float4 *>(p.v0 + col);
+        const float4 ar = *reinterpret_cast<const float4 *>(p.v1 + col);
+        float sl = acc.x * al.x + acc.y * al.y + acc.z * al.z + acc.w * al.w;
+        float sr = acc.x * ar.x + acc.y * ar.y + acc.z * ar.z + acc.w * ar.w;
+        sl += __shfl_xor_sync(0xffffffffu, sl, 1);
+        sr += __shfl_xor_sync(0xffffffffu, sr, 1);
+        sl += __shfl_xor_sync(0xffffffffu, sl, 2);
+        sr += __shfl_xor_sync(0xffffffffu, sr, 2);
+        if (valid) {
+            if (p.round_tf32) { acc.x = tf32_rna(acc.x); acc.y = tf32_rna(acc.y); acc.z = tf32_rna(acc.z); acc.w = tf32_rna(acc.w); }
+            *reinterpret_cast<float4 *>(p.out + row * D_ + col) = acc;
+            if ((col & 15) == 0) {   // first quad of a head: 16 columns per head
+                p.el[row * H_ + (col >> 4)] = sl;
+                p.er[row * H_ + (col >> 4)] = sr;
+            }
+        }
+    } else if (EPI == EPI_FF1) {
+        if (!valid) return;
+        const float4 b = *reinterpret_cast<const float4 *>(p.v0 + col);
+        float4 o;
+        o.x = fmaxf(acc.x + b.x, 0.f); o.y = fmaxf(acc.y + b.y, 0.f);
+        o.z = fmaxf(acc.z + b.z, 0.f); o.w = fmaxf(acc.w + b.w, 0.f);
+        if (p.round_tf32) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
+        *reinterpret_cast<float4 *>(p.out + row * HID_ + col) = o;
+    } else {
+        if (!valid) return;
+        const float4 b = *reinterpret_cast<const float4 *>(p.v0 + col);
+        const float4 sc = *reinterpret_cast<const float4 *>(p.v1 + col);
+        const float4 sh = *reinterpret_cast<const float4 *>(p.v2 + col);
+        const float4 s = *reinterpret_cast<const float4 *>(p.skip + row * D_ + col);
+        float4 o;
+        o.x = (s.x + (acc.x + b.x)) * sc.x + sh.x; o.y = (s.y + (acc.y + b.y)) * sc.y + sh.y;
+        o.z = (s.z + (acc.z + b.z)) * sc.z + sh.z; o.w = (s.w + (acc.w + b.w)) * sc.w + sh.w;
+        if (p.round_tf32) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
+        *reinterpret_cast<float4 *>(p.out + row * D_ + col) = o;
+    }
+}
+
+// ================================================================================================
+// PTX wrappers (sm_100a)
+// ================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives TMEM lane (lane_base + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (ignored for swizzled K-major, 1) | [32,46) SBO>>4 = 1024B>>4
+//   [46,48) version = 1 | [61,64) layout = SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// cute::UMMA::InstrDescriptor: c_format=F32 (1<<4), a/b_format=TF32 (2<<7, 2<<10), K-major A and B,
+// n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ================================================================================================
+// tcgen05 GEMM:  C[M, N_TOTAL] = A[M, K_TOTAL] * W[N_TOTAL, K_TOTAL]^T  with fused epilogue
+// ================================================================================================
+constexpr int BM = 128, BN = 128, BK = 32;           // BK fp32 = 128 bytes = one swizzle row
+constexpr int STAGES = 6;
+constexpr int STAGE_BYTES = (BM + BN) * BK * 4;      // 32 KB
+constexpr int STG_LD = 36;                           // staging row stride (floats): conflict-free quarter-warps
+constexpr int STG_BYTES_PER_WARP = 32 * STG_LD * 4;
+constexpr int GEMM_THREADS = 192;                    // warp0 TMA, warp1 MMA/TMEM, warps 2..5 epilogue
+constexpr int TMEM_COLS = 256;                       // two 128-column fp32 accumulators
+constexpr size_t GEMM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP + 256;
+
+template <int N_TOTAL, int K_TOTAL, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams p) {
+    constexpr int KB = K_TOTAL / BK;
+    constexpr int NB = N_TOTAL / BN;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char *stage_base = smem;
+    float *staging = reinterpret_cast<float *>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP);
+    uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m_tiles = (p.M + BM - 1) / BM;
+    const int64_t n_work = m_tiles * NB;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int m_blk = (int)(w / NB), n_blk = (int)(w % NB);
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char *sa = stage_base + (size_t)stage * STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    tma_load_2d(&tmA, &full[stage], sa, kb * BK, m_blk * BM);
+                    tma_load_2d(&tmB, &full[stage], sa + BM * BK * 4, kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
+                    const uint64_t da = make_sw128_kmajor_desc(sa);
+                    const uint64_t db = make_sw128_kmajor_desc(sa + BM * BK * 4);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {      // UMMA_K = 8 for tf32: 32 bytes along K
+                        umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty[stage]);              // frees the smem slot when these MMAs finish
+                    if (kb == KB - 1) umma_commit(&tfull[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue warps
+        const int q = warp & 3;                               // TMEM lane quarter this warp may access
+        float *stg = staging + (size_t)(warp - 2) * 32 * STG_LD;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int m_blk = (int)(w / NB), n_blk = (int)(w % NB);
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)                   // thread == row: 8 x float4 into its staging row
+                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {              // 4 rows per pass, 8 lanes (x float4) per row
+                    const int r = it * 4 + (lane >> 3);
+                    const float4 a4 = *reinterpret_cast<const float4 *>(stg + r * STG_LD + 4 * (lane & 7));
+                    const int64_t row = (int64_t)m_blk * BM + q * 32 + r;
+                    const int col = n_blk * BN + c * 32 + 4 * (lane & 7);
+                    epilogue_quad<EPI>(p, row, col, a4, row < p.M);
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// row-major fp32 [rows, cols] -> box [128 rows, 32 cols], 128B swizzle, zero fill out of bounds
+int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    GNNGLS_REQUIRE(fn, GNNGLS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    GNNGLS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, GNNGLS_ERR_BAD_ARG, "TMA operand not 16-byte aligned");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GNNGLS_REQUIRE(r == CUDA_SUCCESS, GNNGLS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return GNNGLS_OK;
+}
+
+template <int N_TOTAL, int K_TOTAL, int EPI>
+int launch_tc_gemm(const float *A, const float *W, const EpiParams &p, cudaStream_t st) {
+    CUtensorMap tmA, tmB;
+    if (int rc = make_map(&tmA, A, (uint64_t)p.M, K_TOTAL)) return rc;
+    if (int rc = make_map(&tmB, W, N_TOTAL, K_TOTAL)) return rc;
+    auto kern = gemm_tf32_kernel<N_TOTAL, K_TOTAL, EPI>;
+    GNNGLS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    const int64_t work = ((p.M + BM - 1) / BM) * (N_TOTAL / BN);
+    const int sms = gnngls::device_sm_count();
+    const int grid = (int)(work < sms ? work : sms);
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
+    GNNGLS_LAUNCH_OK("gemm_tf32_kernel");
+    return GNNGLS_OK;
+}
+
+// ================================================================================================
+// SIMT fp32 cross-check GEMM (debug): 64x64 tile, 256 threads, 4x4 micro-tile with the 4 columns
+// contiguous so the shared epilogue_quad() applies unchanged.
+// ================================================================================================
+template <int N_TOTAL, int K_TOTAL, int EPI>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const float *__restrict__ A, const float *__restrict__ W, const EpiParams p) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Ws[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // tx: column quad, ty: row quad
+    const int64_t row0 = (int64_t)blockIdx.x * 64;
+    const int col0 = blockIdx.y * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K_TOTAL; k0 += 16) {
+        for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) {
+            const int r = idx >> 4, k = idx & 15;
+            const int64_t gr = row0 + r;
+            As[k][r] = gr < p.M ? A[gr * K_TOTAL + k0 + k] : 0.f;
+            Ws[k][r] = W[(int64_t)(col0 + r) * K_TOTAL + k0 + k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Ws[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    // lanes of a warp: tx = lane & 15 -> 16 consecutive quads of one row => groups of 4 lanes share a head
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t row = row0 + ty * 4 + i;
+        epilogue_quad<EPI>(p, row, col0 + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]), row < p.M);
+    }
+}
+
+template <int N_TOTAL, int K_TOTAL, int EPI>
+int launch_simt_gemm(const float *A, const float *W, const EpiParams &p, cudaStream_t st) {
+    dim3 grid((unsigned)((p.M + 63) / 64), N_TOTAL / 64);
+    gemm_simt_kernel<N_TOTAL, K_TOTAL, EPI><<<grid, 256, 0, st>>>(A, W, p);
+    GNNGLS_LAUNCH_OK("gemm_simt_kernel");
+    return GNNGLS_OK;
+}
+
+// ================================================================================================
+// embed_layer / decision_layer
+// ================================================================================================
+__global__ void embed_kernel(const float *__restrict__ x, int64_t M, int in_dim, const float *__restrict__ W,
+                             const float *__restrict__ b, float *__restrict__ h, int round_tf32) {
+    // one warp per node, lane owns 4 output channels
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t m = warp0; m < M; m += nwarps) {
+        float4 o = *reinterpret_cast<const float4 *>(b + 4 * lane);
+        for (int k = 0; k < in_dim; ++k) {
+            const float xv = x[m * in_dim + k];
+            o.x = fmaf(xv, W[(4 * lane + 0) * in_dim + k], o.x);
+            o.y = fmaf(xv, W[(4 * lane + 1) * in_dim + k], o.y);
+            o.z = fmaf(xv, W[(4 * lane + 2) * in_dim + k], o.z);
+            o.w = fmaf(xv, W[(4 * lane + 3) * in_dim + k], o.w);
+        }
+        if (round_tf32) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
+        *reinterpret_cast<float4 *>(h + m * D_ + 4 * lane) = o;
+    }
+}
+
+__global__ void decision_kernel(const float *__restrict__ h, int64_t M, int out_dim, const float *__restrict__ Wd,
+                                const float *__restrict__ bd, float *__restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t m = warp0; m < M; m += nwarps) {
+        const float4 v = *reinterpret_cast<const float4 *>(h + m * D_ + 4 * lane);
+        for (int o = 0; o < out_dim; ++o) {
+            const float4 w = *reinterpret_cast<const float4 *>(Wd + o * D_ + 4 * lane);
+            float s = v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) y[m * out_dim + o] = s + bd[o];
+        }
+    }
+}
+
+int elementwise_grid(int64_t warps_needed, int threads) {
+    const int64_t blocks = (warps_needed * 32 + threads - 1) / threads;
+    const int64_t cap = (int64_t)gnngls::device_sm_count() * 16;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int gnngls_embed_forward(const float *x, int64_t M, int in_dim, const float *W, const float *b, float *h,
+                                    int round_tf32, void *stream) {
+    GNNGLS_REQUIRE(x && W && b && h, GNNGLS_ERR_BAD_ARG, "null pointer argument");
+    GNNGLS_REQUIRE(in_dim >= 1, GNNGLS_ERR_BAD_ARG, "in_dim must be >= 1");
+    if (M <= 0) return GNNGLS_OK;
+    embed_kernel<<<elementwise_grid(M, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, M, in_dim, W, b, h, round_tf32);
+    GNNGLS_LAUNCH_OK("embed_kernel");
+    return GNNGLS_OK;
+}
+
+extern "C" int gnngls_decision_forward(const float *h, int64_t M, int out_dim, const float *Wd, const float *bd,
+                                       float *y, void *stream) {
+    GNNGLS_REQUIRE(h && Wd && bd && y, GNNGLS_ERR_BAD_ARG, "null pointer argument");
+    GNNGLS_REQUIRE(out_dim >= 1, GNNGLS_ERR_BAD_ARG, "out_dim must be >= 1");
+    if (M <= 0) return GNNGLS_OK;
+    decision_kernel<<<elementwise_grid(M, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(h, M, out_dim, Wd, bd, y);
+    GNNGLS_LAUNCH_OK("decision_kernel");
+    return GNNGLS_OK;
+}
+
+extern "C" int gnngls_fc_forward(int impl, const float *h, int64_t M, const float *Wfc, const float *attn_l,
+                                 const float *attn_r, float *ft, float *el, float *er, void *stream) {
+    GNNGLS_REQUIRE(h && Wfc && attn_l && attn_r && ft && el && er, GNNGLS_ERR_BAD_ARG, "null pointer argument");
+    if (M <= 0) return GNNGLS_OK;
+    EpiParams p{};
+    p.M = M; p.out = ft; p.el = el; p.er = er; p.v0 = attn_l; p.v1 = attn_r;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (impl == GNNGLS_DENSE_TCGEN05) { p.round_tf32 = 1; return launch_tc_gemm<D_, D_, EPI_FC>(h, Wfc, p, st); }
+    if (impl == GNNGLS_DENSE_SIMT) { p.round_tf32 = 0; return launch_simt_gemm<D_, D_, EPI_FC>(h, Wfc, p, st); }
+    GNNGLS_REQUIRE(false, GNNGLS_ERR_BAD_ARG, "unknown dense impl %d", impl);
+}
+
+extern "C" size_t gnngls_ff_workspace_bytes(int impl, int64_t M) {
+    (void)impl;
+    return M > 0 ? (size_t)M * HID_ * sizeof(float) : 0;     // hidden activations [M,512]
+}
+
+extern "C" int gnngls_ff_forward(int impl, const float *h1, int64_t M, const float *W1, const float *b1,
+                                 const float *W2, const float *b2, const float *bn_scale, const float *bn_shift,
+                                 float *h_out, void *workspace, size_t workspace_bytes, void *stream) {
+    GNNGLS_REQUIRE(h1 && W1 && b1 && W2 && b2 && bn_scale && bn_shift && h_out, GNNGLS_ERR_BAD_ARG, "null pointer argument");
+    if (M <= 0) return GNNGLS_OK;
+    GNNGLS_REQUIRE(workspace && workspace_bytes >= gnngls_ff_workspace_bytes(impl, M), GNNGLS_ERR_WORKSPACE,
+                   "ff workspace too small: need %zu bytes", gnngls_ff_workspace_bytes(impl, M));
+    float *hid = static_cast<float *>(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    EpiParams p1{};
+    p1.M = M; p1.out = hid; p1.v0 = b1;
+    EpiParams p2{};
+    p2.M = M; p2.out = h_out; p2.v0 = b2; p2.v1 = bn_scale; p2.v2 = bn_shift; p2.skip = h1;
+    if (impl == GNNGLS_DENSE_TCGEN05) {
+        p1.round_tf32 = p2.round_tf32 = 1;
+        if (int rc = launch_tc_gemm<HID_, D_, EPI_FF1>(h1, W1, p1, st)) return rc;
+        return launch_tc_gemm<D_, HID_, EPI_FF2>(hid, W2, p2, st);
+    }
+    if (impl == GNNGLS_DENSE_SIMT) {
+        if (int rc = launch_simt_gemm<HID_, D_, EPI_FF1>(h1, W1, p1, st)) return rc;
+        return launch_simt_gemm<D_, HID_, EPI_FF2>(hid, W2, p2, st);
+    }
+    GNNGLS_REQUIRE(false, GNNGLS_ERR_BAD_ARG, "unknown dense impl %d", impl);
+}

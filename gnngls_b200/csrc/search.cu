@@ -1,0 +1,803 @@
+// Search half of the gnngls hot path on sm_100a: all-pairs / one-to-all move evaluation,
+// local_search and the persistent guided_local_search loop, one CTA per instance.
+//
+// Exactness contract: every fp64 expression is evaluated with explicit
+// round-to-nearest intrinsics in the reference's left-to-right association (this file is also
+// compiled with -fmad=false); the parallel arg-min over (delta, scan rank) equals the
+// reference's sequential first-strict-minimum scan.
+//
+// Reference lines followed (relative to the reference repository root):
+//   gnngls/operators.py:6-147, gnngls/algorithms.py:9-18,111-195, gnngls/__init__.py:17-21.
+#include <cstdint>
+#include <cstring>
+#include "common.h"
+
+namespace {
+
+using gnngls::set_error;
+
+// ----------------------------------------------------------------------------------------------
+// candidate bookkeeping
+// ----------------------------------------------------------------------------------------------
+struct Best {
+    double delta;
+    int key;   // scan rank: (i << 16) | j for a2a, j for o2a; < 0 == none
+    int pad;
+};
+
+// numpy.isclose(0, d): |0 - d| <= atol + rtol * |d|  (operators.py:42)
+__device__ __forceinline__ bool close_to_zero(double d) {
+    const double ad = fabs(d);
+    return ad <= __dadd_rn(1e-8, __dmul_rn(1e-5, ad));
+}
+
+// operators.py:41-46: accept iff delta < best_delta (best starts at 0) and not isclose(0, delta)
+__device__ __forceinline__ void consider(Best &b, double delta, int key, bool fi) {
+    if (delta < 0.0 && !close_to_zero(delta)) {
+        const bool take = (b.key < 0) || (fi ? (key < b.key)
+                                             : (delta < b.delta || (delta == b.delta && key < b.key)));
+        if (take) { b.delta = delta; b.key = key; }
+    }
+}
+
+__device__ __forceinline__ Best pick(Best a, Best b, bool fi) {
+    if (b.key < 0) return a;
+    if (a.key < 0) return b;
+    if (fi) return (a.key < b.key) ? a : b;
+    if (a.delta < b.delta) return a;
+    if (b.delta < a.delta) return b;
+    return (a.key < b.key) ? a : b;
+}
+
+__device__ __forceinline__ Best warp_reduce_best(Best v, bool fi) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Best o;
+        o.delta = __shfl_xor_sync(0xffffffffu, v.delta, off);
+        o.key = __shfl_xor_sync(0xffffffffu, v.key, off);
+        v = pick(v, o, fi);
+    }
+    return v;
+}
+
+// result is returned to every thread; `red` is shared scratch of 33 entries
+__device__ Best block_reduce_best(Best v, bool fi, Best *red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_reduce_best(v, fi);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        Best w;
+        w.delta = 0.0; w.key = -1; w.pad = 0;
+        if (lane < nw) w = red[lane];
+        w = warp_reduce_best(w, fi);
+        if (lane == 0) red[32] = w;
+    }
+    __syncthreads();
+    Best r = red[32];
+    __syncthreads();   // red may be reused immediately by the caller
+    return r;
+}
+
+// ----------------------------------------------------------------------------------------------
+// distance-matrix accessors
+// ----------------------------------------------------------------------------------------------
+struct MatPlain {
+    const double *p;
+    int ld;
+    __device__ __forceinline__ double operator()(int a, int b) const { return p[a * ld + b]; }
+};
+
+// algorithms.py:163-164: edge_weight + k * edge_penalties, evaluated per element on read
+template <typename PenT>
+struct MatPen {
+    const double *p;
+    const PenT *pen;
+    int ld, ldp;
+    double k;
+    __device__ __forceinline__ double operator()(int a, int b) const {
+        return __dadd_rn(p[a * ld + b], __dmul_rn(k, (double)pen[a * ldp + b]));
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// all-pairs sweeps (operators.py:32-50, :129-147): one warp per row i, lanes over j
+// ----------------------------------------------------------------------------------------------
+// two_opt_cost (operators.py:14-29), i<j: ((D[a,c] + D[b,d]) - D[a,b]) - D[c,d]
+//   a=t[i] b=t[i-1] c=t[j] d=t[j-1];  E[p] := D[t[p], t[p-1]] so D[a,b]=E[i], D[c,d]=E[j]
+template <class M>
+__device__ Best sweep_two_opt_a2a(const int *t, int n, const M &D, double *E, bool fi, Best *red) {
+    for (int p = 1 + threadIdx.x; p <= n - 1; p += blockDim.x) E[p] = D(t[p], t[p - 1]);
+    __syncthreads();
+    Best best;
+    best.delta = 0.0; best.key = -1; best.pad = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = 1 + warp; i <= n - 3; i += nw) {
+        const int a = t[i], b = t[i - 1];
+        const double Ei = E[i];
+        for (int j = i + 2 + lane; j <= n - 1; j += 32) {
+            const int c = t[j], d = t[j - 1];
+            double x = __dadd_rn(D(a, c), D(b, d));
+            x = __dsub_rn(x, Ei);
+            x = __dsub_rn(x, E[j]);
+            consider(best, x, (i << 16) | j, fi);
+        }
+    }
+    return block_reduce_best(best, fi, red);
+}
+
+// relocate_cost (operators.py:83-103): (((((-D[a,b]) - D[b,c]) + D[a,c]) - D[d,e]) + D[d,b]) + D[b,e]
+//   a=t[i-1] b=t[i] c=t[i+1]; (d,e) = (t[q],t[q+1]) with q = j if i<j else j-1
+//   E[p] := D[t[p], t[p+1]] so D[a,b]=E[i-1], D[b,c]=E[i], D[d,e]=E[q]
+template <class M>
+__device__ Best sweep_relocate_a2a(const int *t, int n, const M &D, double *E, bool fi, Best *red) {
+    for (int p = threadIdx.x; p <= n - 1; p += blockDim.x) E[p] = D(t[p], t[p + 1]);
+    __syncthreads();
+    Best best;
+    best.delta = 0.0; best.key = -1; best.pad = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = 1 + warp; i <= n - 1; i += nw) {
+        const int a = t[i - 1], b = t[i], c = t[i + 1];
+        double base = __dsub_rn(-E[i - 1], E[i]);
+        base = __dadd_rn(base, D(a, c));
+        for (int j = 1 + lane; j <= n - 1; j += 32) {
+            if (j == i || j == i - 1) continue;   // permutations(.,2) has no i==j; operators.py:135 skips i-j==1
+            const int q = (i < j) ? j : j - 1;
+            const int d = t[q], e = t[q + 1];
+            double x = __dsub_rn(base, E[q]);
+            x = __dadd_rn(x, D(d, b));
+            x = __dadd_rn(x, D(b, e));
+            consider(best, x, (i << 16) | j, fi);
+        }
+    }
+    return block_reduce_best(best, fi, red);
+}
+
+// ----------------------------------------------------------------------------------------------
+// one-to-all scans (operators.py:53-73, :106-126): fixed i, threads over j
+// ----------------------------------------------------------------------------------------------
+template <class M>
+__device__ Best scan_two_opt_o2a(const int *t, int n, const M &D, int i, bool fi, Best *red) {
+    Best best;
+    best.delta = 0.0; best.key = -1; best.pad = 0;
+    for (int j = 1 + threadIdx.x; j <= n - 1; j += blockDim.x) {
+        const int df = i - j;
+        if (df < 2 && df > -2) continue;
+        const int lo = (i < j) ? i : j, hi = (i < j) ? j : i;   // two_opt_cost swaps when j < i
+        const int a = t[lo], b = t[lo - 1], c = t[hi], d = t[hi - 1];
+        double x = __dadd_rn(D(a, c), D(b, d));
+        x = __dsub_rn(x, D(a, b));
+        x = __dsub_rn(x, D(c, d));
+        consider(best, x, j, fi);
+    }
+    return block_reduce_best(best, fi, red);
+}
+
+template <class M>
+__device__ Best scan_relocate_o2a(const int *t, int n, const M &D, int i, bool fi, Best *red) {
+    Best best;
+    best.delta = 0.0; best.key = -1; best.pad = 0;
+    const int a = t[i - 1], b = t[i], c = t[i + 1];
+    double base = __dsub_rn(-D(a, b), D(b, c));
+    base = __dadd_rn(base, D(a, c));
+    for (int j = 1 + threadIdx.x; j <= n - 1; j += blockDim.x) {
+        if (j == i) continue;
+        const int q = (i < j) ? j : j - 1;
+        const int d = t[q], e = t[q + 1];
+        double x = __dsub_rn(base, D(d, e));
+        x = __dadd_rn(x, D(d, b));
+        x = __dadd_rn(x, D(b, e));
+        consider(best, x, j, fi);
+    }
+    return block_reduce_best(best, fi, red);
+}
+
+// ----------------------------------------------------------------------------------------------
+// move application (operators.py:6-11, :76-80); block-wide, ends with the tour consistent
+// ----------------------------------------------------------------------------------------------
+__device__ void apply_two_opt(int *t, int i, int j) {
+    if (j < i) { const int s = i; i = j; j = s; }
+    const int half = (j - i) >> 1;                         // reverse positions i .. j-1
+    for (int p = threadIdx.x; p < half; p += blockDim.x) {
+        const int x = t[i + p], y = t[j - 1 - p];
+        t[i + p] = y; t[j - 1 - p] = x;
+    }
+    __syncthreads();
+}
+
+__device__ void apply_relocate(int *t, int *tmp, int i, int j) {   // pop(i); insert(j, node)
+    const int node = t[i];
+    const int lo = (i < j) ? i : j, hi = (i < j) ? j : i;
+    for (int p = lo + threadIdx.x; p <= hi; p += blockDim.x) {
+        int v;
+        if (p == j) v = node;
+        else v = (i < j) ? t[p + 1] : t[p - 1];
+        tmp[p] = v;
+    }
+    __syncthreads();
+    for (int p = lo + threadIdx.x; p <= hi; p += blockDim.x) t[p] = tmp[p];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void apply_move(int op, int *t, int *tmp, int i, int j) {
+    if (op == GNNGLS_OP_TWO_OPT) apply_two_opt(t, i, j);
+    else apply_relocate(t, tmp, i, j);
+}
+
+// gnngls/__init__.py:17-21: c = 0; c += w for consecutive edges (strictly sequential fp64 sum).
+// Edge weights are gathered in parallel into E, then thread 0 adds them in order.
+template <class M>
+__device__ double tour_cost_seq(const int *t, int n, const M &D, double *E, double *slot) {
+    for (int p = threadIdx.x; p < n; p += blockDim.x) E[p] = D(t[p], t[p + 1]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double c = 0.0;
+        for (int p = 0; p < n; ++p) c = __dadd_rn(c, E[p]);
+        *slot = c;
+    }
+    __syncthreads();
+    return *slot;
+}
+
+// ----------------------------------------------------------------------------------------------
+// shared-memory carve-up
+// ----------------------------------------------------------------------------------------------
+struct Smem {
+    double *D;       // n*ld (only when staged)
+    double *E;       // n+1 per-position edge terms
+    double *slot;    // 4 doubles of block-shared scalars
+    Best *red;       // 33
+    int *tour;       // n+1
+    int *tmp;        // n+1
+    int *best_tour;  // n+1 (GLS only)
+    int *ivars;      // 8 block-shared ints
+    uint16_t *pen;   // n*n (GLS, staged only)
+};
+
+__host__ __device__ inline int ld_for(int n) { return n | 1; }   // odd row stride: column reads hit all banks
+
+__host__ __device__ inline size_t smem_layout(int n, bool stage_d, bool gls, bool stage_pen, Smem *s, unsigned char *base) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+    size_t oD = stage_d ? take(sizeof(double) * (size_t)n * ld_for(n)) : 0;
+    size_t oE = take(sizeof(double) * (n + 1));
+    size_t oS = take(sizeof(double) * 4);
+    size_t oR = take(sizeof(Best) * 33);
+    size_t oT = take(sizeof(int) * (n + 1));
+    size_t oM = take(sizeof(int) * (n + 1));
+    size_t oB = gls ? take(sizeof(int) * (n + 1)) : 0;
+    size_t oI = take(sizeof(int) * 8);
+    size_t oP = (gls && stage_pen) ? take(sizeof(uint16_t) * (size_t)n * n) : 0;
+    if (s) {
+        s->D = stage_d ? reinterpret_cast<double *>(base + oD) : nullptr;
+        s->E = reinterpret_cast<double *>(base + oE);
+        s->slot = reinterpret_cast<double *>(base + oS);
+        s->red = reinterpret_cast<Best *>(base + oR);
+        s->tour = reinterpret_cast<int *>(base + oT);
+        s->tmp = reinterpret_cast<int *>(base + oM);
+        s->best_tour = gls ? reinterpret_cast<int *>(base + oB) : nullptr;
+        s->ivars = reinterpret_cast<int *>(base + oI);
+        s->pen = (gls && stage_pen) ? reinterpret_cast<uint16_t *>(base + oP) : nullptr;
+    }
+    return off;
+}
+
+__device__ void stage_matrix(double *dst, const double *src, int n) {
+    const int ld = ld_for(n);
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int r = idx / n, c = idx - r * n;
+        dst[r * ld + c] = src[idx];
+    }
+}
+
+struct EventLog {
+    double *ev;
+    int max_ev;
+    int count;   // maintained by thread 0 only
+    __device__ __forceinline__ void push(double c) {
+        if (ev && count < max_ev) ev[count] = c;
+        ++count;
+    }
+};
+
+// algorithms.py:111-132.  All threads call; tour in shared memory is updated in place; *cost is
+// a block-shared slot updated by thread 0.  Returns nothing; counters are thread-0 registers.
+template <class M>
+__device__ void local_search_dev(const Smem &s, int n, const M &D, bool fi, double *cost_slot,
+                                 EventLog &log, long long *cnt /* thread-0 local [4] */) {
+    bool improved = true;
+    while (improved) {
+        improved = false;
+#pragma unroll 1
+        for (int op = 0; op < 2; ++op) {
+            Best b = (op == 0) ? sweep_two_opt_a2a(s.tour, n, D, s.E, fi, s.red)
+                               : sweep_relocate_a2a(s.tour, n, D, s.E, fi, s.red);
+            if (threadIdx.x == 0) cnt[op] += 1;
+            if (b.key >= 0) {                                  // delta < 0 by construction
+                improved = true;
+                apply_move(op, s.tour, s.tmp, b.key >> 16, b.key & 0xffff);
+                if (threadIdx.x == 0) {
+                    *cost_slot = __dadd_rn(*cost_slot, b.delta);   // cur_cost += delta (:124)
+                    log.push(*cost_slot);
+                    cnt[3] += 1;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ----------------------------------------------------------------------------------------------
+// kernels
+// ----------------------------------------------------------------------------------------------
+template <bool STAGE_D>
+__global__ void moves_kernel(int op, bool o2a, const double *Dg, int64_t d_stride, const int *tours,
+                             const int *pos, int B, int n, int fi, double *out_delta, int *out_move,
+                             int *out_tours) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem s;
+    smem_layout(n, STAGE_D, false, false, &s, smem_raw);
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const double *Db = Dg + (size_t)b * d_stride;
+        for (int p = threadIdx.x; p <= n; p += blockDim.x) s.tour[p] = tours[(size_t)b * (n + 1) + p];
+        MatPlain D;
+        if (STAGE_D) {
+            if (b == blockIdx.x || d_stride != 0) stage_matrix(s.D, Db, n);
+            D.p = s.D; D.ld = ld_for(n);
+        } else {
+            D.p = Db; D.ld = n;
+        }
+        __syncthreads();
+        Best best;
+        int i_fixed = 0;
+        if (o2a) {
+            i_fixed = pos[b];
+            best = (op == GNNGLS_OP_TWO_OPT) ? scan_two_opt_o2a(s.tour, n, D, i_fixed, fi != 0, s.red)
+                                             : scan_relocate_o2a(s.tour, n, D, i_fixed, fi != 0, s.red);
+        } else {
+            best = (op == GNNGLS_OP_TWO_OPT) ? sweep_two_opt_a2a(s.tour, n, D, s.E, fi != 0, s.red)
+                                             : sweep_relocate_a2a(s.tour, n, D, s.E, fi != 0, s.red);
+        }
+        const bool found = best.key >= 0;
+        const int mi = !found ? -1 : (o2a ? i_fixed : (best.key >> 16));
+        const int mj = !found ? -1 : (o2a ? best.key : (best.key & 0xffff));
+        if (threadIdx.x == 0) {
+            out_delta[b] = found ? best.delta : 0.0;
+            out_move[2 * b] = mi; out_move[2 * b + 1] = mj;
+        }
+        if (out_tours) {
+            if (found) apply_move(op, s.tour, s.tmp, mi, mj);
+            for (int p = threadIdx.x; p <= n; p += blockDim.x) out_tours[(size_t)b * (n + 1) + p] = s.tour[p];
+        }
+        __syncthreads();
+    }
+}
+
+template <bool STAGE_D>
+__global__ void local_search_kernel(const double *Dg, int *tours, double *costs, int B, int n, int fi,
+                                    double *events, int *n_events, int max_events, int *status,
+                                    long long *counters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem s;
+    smem_layout(n, STAGE_D, false, false, &s, smem_raw);
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const double *Db = Dg + (size_t)b * n * n;
+        for (int p = threadIdx.x; p <= n; p += blockDim.x) s.tour[p] = tours[(size_t)b * (n + 1) + p];
+        MatPlain D;
+        if (STAGE_D) { stage_matrix(s.D, Db, n); D.p = s.D; D.ld = ld_for(n); }
+        else { D.p = Db; D.ld = n; }
+        if (threadIdx.x == 0) s.slot[0] = costs[b];
+        __syncthreads();
+        EventLog log{events ? events + (size_t)b * max_events : nullptr, max_events, 0};
+        long long cnt[4] = {0, 0, 0, 0};
+        local_search_dev(s, n, D, fi != 0, &s.slot[0], log, cnt);
+        for (int p = threadIdx.x; p <= n; p += blockDim.x) tours[(size_t)b * (n + 1) + p] = s.tour[p];
+        if (threadIdx.x == 0) {
+            costs[b] = s.slot[0];
+            if (n_events) n_events[b] = log.count;
+            if (status) status[b] = (events && log.count > max_events) ? GNNGLS_INST_EVENTS_TRUNCATED : 0;
+            if (counters) for (int q = 0; q < 4; ++q) counters[4 * (size_t)b + q] = cnt[q];
+        }
+        __syncthreads();
+    }
+}
+
+// guide value of the undirected edge (u,v)
+struct GuideRef {
+    const double *mat;   // [n,n] or null
+    const float *vec;    // [N]  or null
+    int n;
+    __device__ __forceinline__ double operator()(int u, int v) const {
+        if (mat) return mat[u * n + v];
+        const int i = u < v ? u : v, j = u < v ? v : u;
+        return (double)vec[i * (2 * n - i - 1) / 2 + (j - i - 1)];
+    }
+};
+
+struct GlsDev {
+    gnngls_gls_args a;
+};
+
+constexpr int kStallCap = 1 << 16;   // safety cap on perturbation-loop trips per outer iteration
+
+// algorithms.py:135-195.  STAGED: D (fp64) and the penalties (u16) live in shared memory;
+// otherwise both are read from global memory (L2-resident).
+template <bool STAGED>
+__global__ void gls_kernel(const GlsDev P) {
+    const gnngls_gls_args &a = P.a;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n;
+    Smem s;
+    smem_layout(n, STAGED, true, STAGED, &s, smem_raw);
+    const bool fi = a.first_improvement != 0;
+    const size_t nn = (size_t)n * n;
+    if (threadIdx.x == 0) s.ivars[0] = 0;
+
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const double *Db = a.D + (size_t)b * nn;
+        int *pen_g = a.penalties ? a.penalties + (size_t)b * nn : nullptr;
+        int status = 0;
+        // ---- load state
+        for (int p = threadIdx.x; p <= n; p += blockDim.x) s.tour[p] = a.cur_tours[(size_t)b * (n + 1) + p];
+        MatPlain D;
+        if (STAGED) {
+            stage_matrix(s.D, Db, n);
+            D.p = s.D; D.ld = ld_for(n);
+            for (int idx = threadIdx.x; idx < (int)nn; idx += blockDim.x) {
+                int v = (a.resume && pen_g) ? pen_g[idx] : 0;
+                if (v > 65535) { v = 65535; status |= GNNGLS_INST_PENALTY_OVERFLOW; }
+                s.pen[idx] = (uint16_t)v;
+            }
+        } else {
+            D.p = Db; D.ld = n;
+            if (!a.resume) for (int idx = threadIdx.x; idx < (int)nn; idx += blockDim.x) pen_g[idx] = 0;
+        }
+        // slot[0] = cur_cost, slot[1] = best_cost, slot[2] = scratch for tour_cost
+        if (threadIdx.x == 0) {
+            s.slot[0] = a.cur_costs[b];
+            if (a.resume) s.slot[1] = a.best_costs[b];
+        }
+        if (a.resume) for (int p = threadIdx.x; p <= n; p += blockDim.x) s.best_tour[p] = a.best_tours[(size_t)b * (n + 1) + p];
+        __syncthreads();
+        double k;
+        if (a.resume) k = a.k[b];
+        else k = __ddiv_rn(__dmul_rn(0.1, s.slot[0]), (double)n);                // :137
+        EventLog log{a.events ? a.events + (size_t)b * a.max_events : nullptr, a.max_events, 0};
+        long long cnt[4] = {0, 0, 0, 0};
+
+        if (!a.resume) {
+            local_search_dev(s, n, D, fi, &s.slot[0], log, cnt);                  // :142
+            for (int p = threadIdx.x; p <= n; p += blockDim.x) s.best_tour[p] = s.tour[p];   // :143
+            if (threadIdx.x == 0) s.slot[1] = s.slot[0];
+            __syncthreads();
+        }
+
+        for (int it = a.iter_begin; it < a.iter_begin + a.n_iters; ++it) {        // :146 (explicit range)
+            const int gsel = it % a.n_guides;                                     // :147
+            GuideRef guide;
+            guide.n = n;
+            if (a.guide_kind == GNNGLS_GUIDE_MATRIX_F64) {
+                guide.mat = static_cast<const double *>(a.guides) + ((size_t)b * a.n_guides + gsel) * nn;
+                guide.vec = nullptr;
+            } else {
+                guide.mat = nullptr;
+                guide.vec = static_cast<const float *>(a.guides) + ((size_t)b * a.n_guides + gsel) * (nn - n) / 2;
+            }
+            int moves = 0, trips = 0;
+            while (moves < a.perturbation_moves) {                                // :151
+                if (++trips > kStallCap) { status |= GNNGLS_INST_STALLED; break; }
+                // ---- :153-159 arg-max utility over tour edges, first edge wins ties
+                Best u;
+                u.delta = 0.0; u.key = -1; u.pad = 0;
+                for (int p = threadIdx.x; p < n; p += blockDim.x) {
+                    const int x = s.tour[p], y = s.tour[p + 1];
+                    const double pen = STAGED ? (double)s.pen[x * n + y] : (double)pen_g[x * n + y];
+                    const double util = __ddiv_rn(guide(x, y), __dadd_rn(1.0, pen));
+                    // reuse the min-reduction on the negated utility: min(-util), ties -> smaller p
+                    const double neg = -util;
+                    if (u.key < 0 || neg < u.delta) { u.delta = neg; u.key = p; }
+                }
+                u = block_reduce_best(u, false, s.red);
+                const int pe = u.key;
+                const int eu = s.tour[pe], ev = s.tour[pe + 1];
+                __syncthreads();
+                if (threadIdx.x == 0) {                                           // :161
+                    if (STAGED) {
+                        unsigned v = (unsigned)s.pen[eu * n + ev] + 1u;
+                        if (v > 65535u) { v = 65535u; s.ivars[0] = 1; }
+                        s.pen[eu * n + ev] = (uint16_t)v; s.pen[ev * n + eu] = (uint16_t)v;
+                    } else {
+                        const int v = pen_g[eu * n + ev] + 1;
+                        pen_g[eu * n + ev] = v; pen_g[ev * n + eu] = v;
+                    }
+                }
+                __syncthreads();
+                // ---- :163-164 penalised matrix, evaluated on read
+#define GLS_PERTURB(MATPEN)                                                                       \
+    for (int e2 = 0; e2 < 2; ++e2) {                                          /* :167 */          \
+        const int node = e2 == 0 ? eu : ev;                                                       \
+        if (node == 0) continue;                                              /* :168 */          \
+        for (int p = 1 + threadIdx.x; p <= n - 1; p += blockDim.x)            /* :169 */          \
+            if (s.tour[p] == node) s.ivars[1] = p;                                                \
+        __syncthreads();                                                                          \
+        const int i = s.ivars[1];                                                                 \
+        for (int op = 0; op < 2; ++op) {                                      /* :171 */          \
+            Best m = (op == 0) ? scan_two_opt_o2a(s.tour, n, MATPEN, i, fi, s.red)                \
+                               : scan_relocate_o2a(s.tour, n, MATPEN, i, fi, s.red);              \
+            if (threadIdx.x == 0) cnt[2] += 1;                                                    \
+            if (m.key >= 0) {                                                 /* :175-185 */      \
+                apply_move(op, s.tour, s.tmp, i, m.key);                                          \
+                const double c = tour_cost_seq(s.tour, n, D, s.E, &s.slot[2]);                    \
+                if (threadIdx.x == 0) { s.slot[0] = c; log.push(c); cnt[3] += 1; }                \
+                moves += 1;                                                                       \
+            }                                                                                     \
+        }                                                                                         \
+    }
+                if (STAGED) {
+                    MatPen<uint16_t> Dp{s.D, s.pen, ld_for(n), n, k};
+                    GLS_PERTURB(Dp)
+                } else {
+                    MatPen<int> Dp{Db, pen_g, n, n, k};
+                    GLS_PERTURB(Dp)
+                }
+#undef GLS_PERTURB
+            }
+            local_search_dev(s, n, D, fi, &s.slot[0], log, cnt);                  // :188
+            if (s.slot[0] < s.slot[1]) {                                          // :190-191 (block-uniform)
+                for (int p = threadIdx.x; p <= n; p += blockDim.x) s.best_tour[p] = s.tour[p];
+                __syncthreads();
+                if (threadIdx.x == 0) s.slot[1] = s.slot[0];
+            }
+            __syncthreads();
+        }
+
+        // ---- store state
+        for (int p = threadIdx.x; p <= n; p += blockDim.x) {
+            a.cur_tours[(size_t)b * (n + 1) + p] = s.tour[p];
+            a.best_tours[(size_t)b * (n + 1) + p] = s.best_tour[p];
+        }
+        if (STAGED && pen_g) for (int idx = threadIdx.x; idx < (int)nn; idx += blockDim.x) pen_g[idx] = s.pen[idx];
+        if (threadIdx.x == 0) {
+            a.cur_costs[b] = s.slot[0];
+            a.best_costs[b] = s.slot[1];
+            if (!a.resume) a.k[b] = k;
+            if (a.n_events) a.n_events[b] = log.count;
+            if (STAGED && s.ivars[0]) status |= GNNGLS_INST_PENALTY_OVERFLOW;
+            if (a.events && log.count > a.max_events) status |= GNNGLS_INST_EVENTS_TRUNCATED;
+            if (a.status) a.status[b] = status;
+            if (a.counters) for (int q = 0; q < 4; ++q) a.counters[4 * (size_t)b + q] = cnt[q];
+            s.ivars[0] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+// algorithms.py:9-18 + __init__.py:17-21.  One warp per instance.
+__global__ void nn_init_kernel(int guide_kind, const void *guides, const double *Dg, int B, int n, int depot,
+                               int *out_tours, double *out_costs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    double *E = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (n + 1);
+    int *tour = reinterpret_cast<int *>(smem_raw + sizeof(double) * (size_t)wpb * (n + 1)) + (size_t)warp * (n + 1);
+    const size_t nn = (size_t)n * n;
+    for (int b = blockIdx.x * wpb + warp; b < B; b += gridDim.x * wpb) {
+        GuideRef g;
+        g.n = n;
+        g.mat = guide_kind == GNNGLS_GUIDE_MATRIX_F64 ? static_cast<const double *>(guides) + (size_t)b * nn : nullptr;
+        g.vec = guide_kind == GNNGLS_GUIDE_MATRIX_F64 ? nullptr : static_cast<const float *>(guides) + (size_t)b * (nn - n) / 2;
+        unsigned visited = 0;   // bit q <-> node lane + 32*q  (n <= 1024)
+        if ((depot & 31) == lane) visited |= 1u << (depot >> 5);
+        int cur = depot;
+        if (lane == 0) tour[0] = depot;
+        for (int len = 1; len < n; ++len) {
+            double bw = 0.0;
+            int bj = -1;
+            for (int q = 0, j = lane; j < n; ++q, j += 32) {
+                if (visited & (1u << q)) continue;
+                const double w = g(cur, j);
+                if (bj < 0 || w < bw) { bw = w; bj = j; }      // ascending j per lane: first minimum kept
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ow = __shfl_xor_sync(0xffffffffu, bw, off);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+                if (oj >= 0 && (bj < 0 || ow < bw || (ow == bw && oj < bj))) { bw = ow; bj = oj; }
+            }
+            if ((bj & 31) == lane) visited |= 1u << (bj >> 5);
+            if (lane == 0) tour[len] = bj;
+            cur = bj;
+        }
+        if (lane == 0) tour[n] = depot;
+        __syncwarp();
+        for (int p = lane; p <= n; p += 32) out_tours[(size_t)b * (n + 1) + p] = tour[p];
+        if (Dg && out_costs) {
+            const double *Db = Dg + (size_t)b * nn;
+            for (int p = lane; p < n; p += 32) E[p] = Db[(size_t)tour[p] * n + tour[p + 1]];
+            __syncwarp();
+            if (lane == 0) {
+                double c = 0.0;
+                for (int p = 0; p < n; ++p) c = __dadd_rn(c, E[p]);
+                out_costs[b] = c;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void tour_cost_kernel(const double *Dg, const int *tours, int B, int n, double *out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    double *E = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (n + 1);
+    for (int b = blockIdx.x * wpb + warp; b < B; b += gridDim.x * wpb) {
+        const double *Db = Dg + (size_t)b * n * n;
+        const int *t = tours + (size_t)b * (n + 1);
+        for (int p = lane; p < n; p += 32) E[p] = Db[(size_t)t[p] * n + t[p + 1]];
+        __syncwarp();
+        if (lane == 0) {
+            double c = 0.0;
+            for (int p = 0; p < n; ++p) c = __dadd_rn(c, E[p]);
+            out[b] = c;
+        }
+        __syncwarp();
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// launch helpers
+// ----------------------------------------------------------------------------------------------
+int pick_threads(int n) {
+    if (n <= 40) return 64;
+    if (n <= 72) return 128;
+    if (n <= 160) return 256;
+    if (n <= 400) return 512;
+    return 1024;
+}
+
+template <typename K>
+int ensure_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+    return GNNGLS_OK;
+}
+
+int grid_for(int B) {
+    const int cap = gnngls::device_sm_count() * 16;
+    return B < cap ? (B > 0 ? B : 1) : cap;
+}
+
+int check_n(int n) {
+    GNNGLS_REQUIRE(n >= 3 && n <= 1024, GNNGLS_ERR_UNSUPPORTED, "n=%d outside supported range [3,1024]", n);
+    return GNNGLS_OK;
+}
+
+int launch_moves(int op, bool o2a, const double *D, int64_t stride, const int *tours, const int *pos, int B, int n,
+                 int fi, double *out_delta, int *out_move, int *out_tours, cudaStream_t st) {
+    GNNGLS_REQUIRE(op == GNNGLS_OP_TWO_OPT || op == GNNGLS_OP_RELOCATE, GNNGLS_ERR_BAD_ARG, "bad move op %d", op);
+    GNNGLS_REQUIRE(D && tours && out_delta && out_move && (!o2a || pos), GNNGLS_ERR_BAD_ARG, "null pointer argument");
+    GNNGLS_REQUIRE(stride == 0 || stride == (int64_t)n * n, GNNGLS_ERR_BAD_ARG, "d_batch_stride must be 0 or n*n");
+    if (int rc = check_n(n)) return rc;
+    if (B <= 0) return GNNGLS_OK;
+    const int threads = pick_threads(n);
+    const size_t staged = smem_layout(n, true, false, false, nullptr, nullptr);
+    const size_t plain = smem_layout(n, false, false, false, nullptr, nullptr);
+    const size_t limit = (size_t)gnngls::device_max_optin_smem();
+    if (staged <= limit) {
+        if (int rc = ensure_smem(moves_kernel<true>, staged)) return rc;
+        moves_kernel<true><<<grid_for(B), threads, staged, st>>>(op, o2a, D, stride, tours, pos, B, n, fi, out_delta,
+                                                                out_move, out_tours);
+    } else {
+        moves_kernel<false><<<grid_for(B), threads, plain, st>>>(op, o2a, D, stride, tours, pos, B, n, fi, out_delta,
+                                                                out_move, out_tours);
+    }
+    GNNGLS_LAUNCH_OK("moves_kernel");
+    return GNNGLS_OK;
+}
+
+}  // namespace
+
+extern "C" int gnngls_moves_eval_a2a(int op, const double *D, int64_t d_batch_stride, const int32_t *tours, int B,
+                                     int n, int first_improvement, double *out_delta, int32_t *out_move,
+                                     int32_t *out_tours, void *stream) {
+    return launch_moves(op, false, D, d_batch_stride, tours, nullptr, B, n, first_improvement, out_delta, out_move,
+                        out_tours, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gnngls_moves_eval_o2a(int op, const double *D, int64_t d_batch_stride, const int32_t *tours,
+                                     const int32_t *pos, int B, int n, int first_improvement, double *out_delta,
+                                     int32_t *out_move, int32_t *out_tours, void *stream) {
+    return launch_moves(op, true, D, d_batch_stride, tours, pos, B, n, first_improvement, out_delta, out_move,
+                        out_tours, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gnngls_local_search_batch(const double *D, int32_t *tours, double *costs, int B, int n,
+                                         int first_improvement, double *events, int32_t *n_events, int max_events,
+                                         int32_t *status, int64_t *counters, void *stream) {
+    GNNGLS_REQUIRE(D && tours && costs, GNNGLS_ERR_BAD_ARG, "null pointer argument");
+    GNNGLS_REQUIRE(max_events >= 0, GNNGLS_ERR_BAD_ARG, "max_events < 0");
+    if (int rc = check_n(n)) return rc;
+    if (B <= 0) return GNNGLS_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int threads = pick_threads(n);
+    const size_t staged = smem_layout(n, true, false, false, nullptr, nullptr);
+    const size_t plain = smem_layout(n, false, false, false, nullptr, nullptr);
+    if (staged <= (size_t)gnngls::device_max_optin_smem()) {
+        if (int rc = ensure_smem(local_search_kernel<true>, staged)) return rc;
+        local_search_kernel<true><<<grid_for(B), threads, staged, st>>>(
+            D, tours, costs, B, n, first_improvement, events, n_events, max_events, status,
+            reinterpret_cast<long long *>(counters));
+    } else {
+        local_search_kernel<false><<<grid_for(B), threads, plain, st>>>(
+            D, tours, costs, B, n, first_improvement, events, n_events, max_events, status,
+            reinterpret_cast<long long *>(counters));
+    }
+    GNNGLS_LAUNCH_OK("local_search_kernel");
+    return GNNGLS_OK;
+}
+
+extern "C" size_t gnngls_sizeof_gls_args(void) { return sizeof(gnngls_gls_args); }
+
+extern "C" int gnngls_gls_batch(const gnngls_gls_args *args, void *stream) {
+    GNNGLS_REQUIRE(args, GNNGLS_ERR_BAD_ARG, "null args");
+    const gnngls_gls_args &a = *args;
+    GNNGLS_REQUIRE(a.D && a.guides && a.cur_tours && a.cur_costs && a.best_tours && a.best_costs && a.k,
+                   GNNGLS_ERR_BAD_ARG, "null pointer argument");
+    GNNGLS_REQUIRE(a.n_guides >= 1 && a.n_iters >= 0 && a.iter_begin >= 0 && a.perturbation_moves >= 0 &&
+                       a.max_events >= 0,
+                   GNNGLS_ERR_BAD_ARG, "bad scalar argument");
+    GNNGLS_REQUIRE(a.guide_kind == GNNGLS_GUIDE_MATRIX_F64 || a.guide_kind == GNNGLS_GUIDE_EDGEVEC_F32,
+                   GNNGLS_ERR_BAD_ARG, "bad guide_kind %d", a.guide_kind);
+    GNNGLS_REQUIRE(!a.resume || a.penalties, GNNGLS_ERR_BAD_ARG, "resume needs a penalties buffer");
+    if (int rc = check_n(a.n)) return rc;
+    GNNGLS_REQUIRE(a.n >= 4 || a.n_iters == 0 || a.perturbation_moves == 0, GNNGLS_ERR_UNSUPPORTED,
+                   "guided_local_search cannot make progress for n < 4 (the reference spins forever)");
+    if (a.B <= 0) return GNNGLS_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GlsDev P;
+    P.a = a;
+    const int threads = pick_threads(a.n);
+    const size_t staged = smem_layout(a.n, true, true, true, nullptr, nullptr);
+    const size_t plain = smem_layout(a.n, false, true, false, nullptr, nullptr);
+    if (staged <= (size_t)gnngls::device_max_optin_smem()) {
+        if (int rc = ensure_smem(gls_kernel<true>, staged)) return rc;
+        gls_kernel<true><<<grid_for(a.B), threads, staged, st>>>(P);
+    } else {
+        GNNGLS_REQUIRE(a.penalties, GNNGLS_ERR_WORKSPACE,
+                       "n=%d does not fit shared memory: a [B,n,n] int32 penalties buffer is required", a.n);
+        gls_kernel<false><<<grid_for(a.B), threads, plain, st>>>(P);
+    }
+    GNNGLS_LAUNCH_OK("gls_kernel");
+    return GNNGLS_OK;
+}
+
+extern "C" int gnngls_nn_init_batch(int guide_kind, const void *guide, const double *D, int B, int n, int depot,
+                                    int32_t *out_tours, double *out_costs, void *stream) {
+    GNNGLS_REQUIRE(guide && out_tours, GNNGLS_ERR_BAD_ARG, "null pointer argument");
+    GNNGLS_REQUIRE(guide_kind == GNNGLS_GUIDE_MATRIX_F64 || guide_kind == GNNGLS_GUIDE_EDGEVEC_F32, GNNGLS_ERR_BAD_ARG,
+                   "bad guide_kind %d", guide_kind);
+    GNNGLS_REQUIRE(n >= 2 && n <= 1024, GNNGLS_ERR_UNSUPPORTED, "n=%d outside supported range [2,1024]", n);
+    GNNGLS_REQUIRE(depot >= 0 && depot < n, GNNGLS_ERR_BAD_ARG, "depot out of range");
+    if (B <= 0) return GNNGLS_OK;
+    const int wpb = 4;
+    const size_t smem = (sizeof(double) + sizeof(int)) * (size_t)wpb * (n + 1) + 16;
+    if (int rc = ensure_smem(nn_init_kernel, smem)) return rc;
+    const int blocks = (B + wpb - 1) / wpb;
+    nn_init_kernel<<<blocks, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(guide_kind, guide, D, B, n, depot,
+                                                                              out_tours, out_costs);
+    GNNGLS_LAUNCH_OK("nn_init_kernel");
+    return GNNGLS_OK;
+}
+
+extern "C" int gnngls_tour_cost_batch(const double *D, const int32_t *tours, int B, int n, double *out_costs,
+                                      void *stream) {
+    GNNGLS_REQUIRE(D && tours && out_costs, GNNGLS_ERR_BAD_ARG, "null pointer argument");
+    GNNGLS_REQUIRE(n >= 1 && n <= 65535, GNNGLS_ERR_UNSUPPORTED, "n=%d unsupported", n);
+    if (B <= 0) return GNNGLS_OK;
+    const int wpb = 4;
+    const size_t smem = sizeof(double) * (size_t)wpb * (n + 1);
+    if (int rc = ensure_smem(tour_cost_kernel, smem)) return rc;
+    tour_cost_kernel<<<(B + wpb - 1) / wpb, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(D, tours, B, n,
+                                                                                              out_costs);
+    GNNGLS_LAUNCH_OK("tour_cost_kernel");
+    return GNNGLS_OK;
+}

@@ -1,0 +1,256 @@
+"""Drop-in for /root/reference/gnngls/models.py on B200.
+
+Same class names, constructor arguments, ``forward(G, x)`` signature and module tree, so a
+``state_dict`` saved by the reference (scripts/train.py:60-67) loads with ``strict=True`` — including
+checkpoints trained with DGL >= 0.7 whose GATConv carries an extra ``bias``.  The forward pass is
+inference only (eval-mode BatchNorm) and runs entirely in hand-written sm_100a kernels through the
+C ABI (include/gnngls_b200.h); per AttentionLayer (models.py:38-41):
+
+    fc (+el/er)  ->  edge-softmax/aggregate + skip + BN1  ->  FF + skip + BN2
+
+There is no CPU or eager-PyTorch fallback: tensors must live on a CUDA device.
+"""
+import ctypes
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib, _ops
+from ._timing import stage
+from .graph import LineGraph
+
+HIDDEN_DIM = 512        # hard-coded in the reference (models.py:60)
+_SUPPORTED = dict(embed_dim=128, n_heads=8)
+
+
+def _dense_impl_default():
+    name = os.environ.get('GNNGLS_DENSE_IMPL', 'tcgen05').lower()
+    if name not in ('tcgen05', 'simt'):
+        raise ValueError('GNNGLS_DENSE_IMPL must be tcgen05 or simt')
+    return name
+
+
+class SkipConnection(nn.Module):
+    """models.py:5-15.  Kept for the module tree; AttentionLayer fuses the add into its kernels."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, x, G=None):
+        if G is not None:
+            y = self.module(G, x).view(G.number_of_nodes(), -1)
+        else:
+            y = self.module(x)
+        return x + y
+
+
+class GATConv(nn.Module):
+    """Parameter holder + standalone forward with dgl.nn.GATConv(in, out, heads) semantics
+    (feat_drop=attn_drop=0, negative_slope=0.2, no residual, no activation)."""
+
+    def __init__(self, in_feats, out_feats, num_heads, negative_slope=0.2):
+        super().__init__()
+        self._in_feats, self._out_feats, self._num_heads = in_feats, out_feats, num_heads
+        if negative_slope != 0.2:
+            raise NotImplementedError('kernels are built for negative_slope=0.2')
+        self.fc = nn.Linear(in_feats, out_feats * num_heads, bias=False)
+        self.attn_l = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.attn_r = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.bias = None      # DGL 0.6.1 (the pinned version) has no bias; created on load if present
+        gain = nn.init.calculate_gain('relu')
+        nn.init.xavier_normal_(self.fc.weight, gain=gain)
+        nn.init.xavier_normal_(self.attn_l, gain=gain)
+        nn.init.xavier_normal_(self.attn_r, gain=gain)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        if prefix + 'bias' in state_dict and self.bias is None:
+            self.bias = nn.Parameter(torch.zeros(self._out_feats * self._num_heads, device=self.fc.weight.device,
+                                                 dtype=self.fc.weight.dtype))
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def forward(self, G, feat):
+        M = G.number_of_nodes()
+        zero = torch.zeros(M, self._in_feats, dtype=torch.float32, device=feat.device)
+        one = torch.ones(self._in_feats, dtype=torch.float32, device=feat.device)
+        out = _gat_block(G, feat.contiguous(), zero, self.fc.weight.detach().contiguous(),
+                         self.attn_l.detach().reshape(-1).contiguous(), self.attn_r.detach().reshape(-1).contiguous(),
+                         None if self.bias is None else self.bias.detach().contiguous(), one,
+                         torch.zeros_like(one), _ops.DENSE_SIMT if _dense_impl_default() == 'simt' else _ops.DENSE_TCGEN05,
+                         'auto', {})
+        return out.view(M, self._num_heads, self._out_feats)
+
+
+def tf32_round(t):
+    """Round fp32 to TF32 (10-bit mantissa), nearest with ties away from zero == PTX cvt.rna.tf32.f32.
+    The tcgen05 kind::tf32 MMA ignores the low 13 mantissa bits of its operands; weights are rounded
+    here once so that this truncation is exact (activations are rounded by the producing kernels)."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _bn_affine(bn):
+    """Eval-mode BatchNorm1d as y = x*scale + shift (models.py:27,35)."""
+    with torch.no_grad():
+        scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+        shift = bn.bias.float() - bn.running_mean.float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def _buf(ws, name, shape, dtype, device):
+    t = ws.get(name)
+    numel = 1
+    for s in shape:
+        numel *= s
+    if t is None or t.numel() < numel or t.dtype != dtype or t.device != device:
+        t = torch.empty(numel, dtype=dtype, device=device)
+        ws[name] = t
+    return t[:numel].view(*shape)
+
+
+def _gat_block(G, h, skip, Wfc, al, ar, bias, bn_scale, bn_shift, dense_impl, gat_impl, ws):
+    """fc + aggregate(+skip+BN1).  Returns h1 [M,128]."""
+    lib = _lib.load()
+    M, dev = h.shape[0], h.device
+    st = _ops._stream()
+    ft = _buf(ws, 'ft', (M, 128), torch.float32, dev)
+    el = _buf(ws, 'el', (M, 8), torch.float32, dev)
+    er = _buf(ws, 'er', (M, 8), torch.float32, dev)
+    h1 = _buf(ws, 'h1', (M, 128), torch.float32, dev)
+    p = _ops._ptr
+    rnd = 1 if dense_impl == _ops.DENSE_TCGEN05 else 0
+    with stage('fc'):
+        _lib.check(lib.gnngls_fc_forward(dense_impl, p(h), M, p(Wfc), p(al), p(ar), p(ft), p(el), p(er), st))
+    use_kn = gat_impl == 'kn' or (gat_impl == 'auto' and G.kind == 'kn' and G.n <= 380)
+    if use_kn:
+        if G.kind != 'kn':
+            raise ValueError("gat_impl='kn' needs a LineGraph.complete graph")
+        nbytes = lib.gnngls_gat_kn_workspace_bytes(G.batch_size, G.n)
+        wk = _buf(ws, 'gat_ws', (nbytes,), torch.uint8, dev)
+        with stage('gat_kn'):
+            _lib.check(lib.gnngls_gat_aggregate_kn(G.batch_size, G.n, p(ft), p(el), p(er), p(skip), p(bias),
+                                                   p(bn_scale), p(bn_shift), p(h1), rnd, p(wk), nbytes, st))
+    else:
+        indptr, indices = G.csr()
+        with stage('gat_csr'):
+            _lib.check(lib.gnngls_gat_aggregate_csr(p(indptr), p(indices), M, p(ft), p(el), p(er), p(skip), p(bias),
+                                                    p(bn_scale), p(bn_shift), p(h1), rnd, st))
+    return h1
+
+
+class AttentionLayer(nn.Module):
+    """models.py:18-41."""
+
+    def __init__(self, embed_dim, n_heads, hidden_dim):
+        super().__init__()
+        self.message_passing = SkipConnection(GATConv(embed_dim, embed_dim // n_heads, n_heads))
+        self.feed_forward = nn.Sequential(
+            nn.BatchNorm1d(embed_dim),
+            SkipConnection(nn.Sequential(nn.Linear(embed_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, embed_dim))),
+            nn.BatchNorm1d(embed_dim),
+        )
+        self._dims = (embed_dim, n_heads, hidden_dim)
+
+    def _device_params(self):
+        gat = self.message_passing.module
+        ff = self.feed_forward[1].module
+        s1, t1 = _bn_affine(self.feed_forward[0])
+        s2, t2 = _bn_affine(self.feed_forward[2])
+        f = lambda t: t.detach().float().contiguous()      # noqa: E731
+        d = dict(Wfc=f(gat.fc.weight), al=f(gat.attn_l).reshape(-1), ar=f(gat.attn_r).reshape(-1),
+                 gbias=None if gat.bias is None else f(gat.bias), s1=s1, t1=t1,
+                 W1=f(ff[0].weight), b1=f(ff[0].bias), W2=f(ff[2].weight), b2=f(ff[2].bias), s2=s2, t2=t2)
+        for k in ('Wfc', 'W1', 'W2'):
+            d[k + '_tf32'] = tf32_round(d[k])
+        return d
+
+    def forward(self, G, x, _params=None, _ws=None, _dense_impl=None, _gat_impl='auto', _out=None):
+        if self.training:
+            raise NotImplementedError('gnngls_b200 implements the inference path only: call model.eval()')
+        if self._dims != (128, 8, 512):
+            raise NotImplementedError('kernels are specialised for embed_dim=128, n_heads=8, hidden_dim=512')
+        lib = _lib.load()
+        prm = _params if _params is not None else self._device_params()
+        ws = _ws if _ws is not None else {}
+        impl = _dense_impl if _dense_impl is not None else (
+            _ops.DENSE_SIMT if _dense_impl_default() == 'simt' else _ops.DENSE_TCGEN05)
+        x = x.contiguous()
+        M, dev = x.shape[0], x.device
+        sfx = '_tf32' if impl == _ops.DENSE_TCGEN05 else ''
+        h1 = _gat_block(G, x, x, prm['Wfc' + sfx], prm['al'], prm['ar'], prm['gbias'], prm['s1'], prm['t1'], impl, _gat_impl, ws)
+        nbytes = lib.gnngls_ff_workspace_bytes(impl, M)
+        wk = _buf(ws, 'ff_ws', (nbytes,), torch.uint8, dev)
+        out = _out if _out is not None else torch.empty(M, 128, dtype=torch.float32, device=dev)
+        p = _ops._ptr
+        with stage('ff'):
+            _lib.check(lib.gnngls_ff_forward(impl, p(h1), M, p(prm['W1' + sfx]), p(prm['b1']), p(prm['W2' + sfx]),
+                                             p(prm['b2']), p(prm['s2']), p(prm['t2']), p(out), p(wk), nbytes,
+                                             _ops._stream()))
+        return out
+
+
+class EdgePropertyPredictionModel(nn.Module):
+    """models.py:44-70.  NB: like the reference, the number of AttentionLayers is ``n_heads``
+    (models.py:60 iterates ``range(n_heads)``); ``n_layers`` is accepted and ignored."""
+
+    def __init__(self, in_dim, embed_dim, out_dim, n_layers, n_heads=1):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.embed_layer = nn.Linear(in_dim, embed_dim)
+        self.message_passing_layers = nn.Sequential(
+            *(AttentionLayer(embed_dim, n_heads, HIDDEN_DIM) for _ in range(n_heads)))
+        self.decision_layer = nn.Linear(embed_dim, out_dim)
+        self.dense_impl = None      # None -> $GNNGLS_DENSE_IMPL or 'tcgen05'
+        self.gat_impl = 'auto'      # 'auto' | 'kn' | 'csr'
+        self._cache_sig, self._cache = None, None
+        self._ws = {}
+
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _prepared(self):
+        sig = self._signature()
+        if sig != self._cache_sig:
+            f = lambda t: t.detach().float().contiguous()  # noqa: E731
+            self._cache = dict(We=f(self.embed_layer.weight), be=f(self.embed_layer.bias),
+                               Wd=f(self.decision_layer.weight), bd=f(self.decision_layer.bias),
+                               layers=[l._device_params() for l in self.message_passing_layers])
+            self._cache_sig = sig
+        return self._cache
+
+    def forward(self, G, x):
+        if self.training:
+            raise NotImplementedError('gnngls_b200 implements the inference path only: call model.eval()')
+        if not isinstance(G, LineGraph):
+            raise TypeError('G must be a gnngls_b200.LineGraph (LineGraph.complete(n, batch) or .from_edges(...))')
+        if not x.is_cuda:
+            raise RuntimeError('gnngls_b200 has no CPU path: move the model, graph and features to a CUDA device')
+        n_heads = len(self.message_passing_layers)
+        if self.embed_dim != _SUPPORTED['embed_dim'] or n_heads != _SUPPORTED['n_heads']:
+            raise NotImplementedError('kernels are specialised for embed_dim=128, n_heads=8 (the shipped params.json)')
+        lib = _lib.load()
+        prm = self._prepared()
+        name = self.dense_impl or _dense_impl_default()
+        impl = _ops.DENSE_SIMT if name == 'simt' else _ops.DENSE_TCGEN05
+        x = x.detach().to(torch.float32).contiguous()
+        M, dev = x.shape[0], x.device
+        if M != G.number_of_nodes():
+            raise ValueError(f'features have {M} rows but the graph has {G.number_of_nodes()} nodes')
+        in_dim, out_dim = self.embed_layer.in_features, self.decision_layer.out_features
+        p = _ops._ptr
+        with torch.cuda.device(dev):
+            ha = _buf(self._ws, 'ha', (M, 128), torch.float32, dev)
+            hb = _buf(self._ws, 'hb', (M, 128), torch.float32, dev)
+            with stage('embed'):
+                _lib.check(lib.gnngls_embed_forward(p(x), M, in_dim, p(prm['We']), p(prm['be']), p(ha),
+                                                    1 if impl == _ops.DENSE_TCGEN05 else 0, _ops._stream()))
+            cur, nxt = ha, hb
+            for layer, lp in zip(self.message_passing_layers, prm['layers']):
+                layer(G, cur, _params=lp, _ws=self._ws, _dense_impl=impl, _gat_impl=self.gat_impl, _out=nxt)
+                cur, nxt = nxt, cur
+            y = torch.empty(M, out_dim, dtype=torch.float32, device=dev)
+            with stage('decision'):
+                _lib.check(lib.gnngls_decision_forward(p(cur), M, out_dim, p(prm['Wd']), p(prm['bd']), p(y),
+                                                       _ops._stream()))
+        return y

@@ -1,0 +1,204 @@
+/* gnngls_b200 — C ABI of the B200-native gnngls inference hot path.
+ *
+ * The reference (proroklab/gnngls) is pure Python and has no FFI of its own; this header is
+ * the boundary a maintainer would bind (ctypes stub in INTEGRATION.md) to replace, function by
+ * function, the reference code cited beside each entry point (paths relative to the reference
+ * repository root).
+ *
+ * Conventions
+ *  - every pointer is a caller-owned DEVICE pointer unless the name ends in _host;
+ *  - `stream` is a cudaStream_t passed as void*; all entry points are asynchronous w.r.t. the
+ *    host and never allocate device memory (workspaces are caller-provided, sizes are queried);
+ *  - return value: 0 on success, negative gnngls_status on failure; a human-readable message
+ *    for the calling thread's last failure is available from gnngls_last_error_string();
+ *  - tours are int32[n+1] with tour[0] == tour[n] == 0 (the depot), distance matrices are
+ *    row-major fp64 [n,n]; batches are dense leading dimensions.
+ */
+#ifndef GNNGLS_B200_H_
+#define GNNGLS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNNGLS_B200_ABI_VERSION 1
+
+typedef enum gnngls_status {
+    GNNGLS_OK = 0,
+    GNNGLS_ERR_BAD_ARG = -1,
+    GNNGLS_ERR_UNSUPPORTED = -2,
+    GNNGLS_ERR_CUDA = -3,
+    GNNGLS_ERR_WORKSPACE = -4
+} gnngls_status;
+
+typedef enum gnngls_move_op {
+    GNNGLS_OP_TWO_OPT = 0,   /* gnngls/operators.py:6-29  */
+    GNNGLS_OP_RELOCATE = 1   /* gnngls/operators.py:76-103 */
+} gnngls_move_op;
+
+/* How a guide (edge attribute used for the GLS utility / nearest-neighbour init) is stored. */
+typedef enum gnngls_guide_kind {
+    GNNGLS_GUIDE_MATRIX_F64 = 0,  /* [B, n_guides, n, n] fp64, symmetric                          */
+    GNNGLS_GUIDE_EDGEVEC_F32 = 1  /* [B, n_guides, n(n-1)/2] fp32, line-graph node order (i<j);    *
+                                   * widened to fp64 on read, as scripts/test.py:81-83 does         */
+} gnngls_guide_kind;
+
+/* per-instance status bits written by the search kernels */
+#define GNNGLS_INST_EVENTS_TRUNCATED 1   /* more events than max_events; count is still exact */
+#define GNNGLS_INST_PENALTY_OVERFLOW 2
+#define GNNGLS_INST_STALLED 4            /* perturbation loop hit the safety cap (reference would spin) */
+
+int gnngls_abi_version(void);
+const char *gnngls_last_error_string(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Move evaluation — gnngls/operators.py:32-50 (two_opt_a2a), :129-147 (relocate_a2a),
+ * :53-73 (two_opt_o2a), :106-126 (relocate_o2a).
+ * One CTA per (instance); fp64 deltas in the reference's association order, no FMA; the winner
+ * equals the reference's sequential first-strict-minimum scan.
+ *   D            [B,n,n] fp64, or one [n,n] matrix shared by the batch when d_batch_stride == 0
+ *   tours        [B,n+1] int32
+ *   pos          [B] int32 (o2a only): the fixed index i, 0 < i < n
+ *   out_delta    [B] fp64  : best delta, or 0.0 when no improving move exists
+ *   out_move     [B,2] int32: (i,j) of the chosen move, (-1,-1) when none
+ *   out_tours    [B,n+1] int32 or NULL: tour after applying the move (copy of input when none)
+ * ------------------------------------------------------------------------------------------- */
+int gnngls_moves_eval_a2a(int op, const double *D, int64_t d_batch_stride, const int32_t *tours,
+                          int B, int n, int first_improvement,
+                          double *out_delta, int32_t *out_move, int32_t *out_tours, void *stream);
+
+int gnngls_moves_eval_o2a(int op, const double *D, int64_t d_batch_stride, const int32_t *tours,
+                          const int32_t *pos, int B, int n, int first_improvement,
+                          double *out_delta, int32_t *out_move, int32_t *out_tours, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * local_search — gnngls/algorithms.py:111-132.  tours/costs are updated in place.
+ *   events   [B,max_events] fp64 or NULL: cost after every accepted move (search_progress['cost'])
+ *   n_events [B] int32 or NULL;  status [B] int32 or NULL (GNNGLS_INST_* bits)
+ *   counters [B,4] int64 or NULL: {two-opt sweeps, relocate sweeps, o2a scans, accepted moves}
+ * ------------------------------------------------------------------------------------------- */
+int gnngls_local_search_batch(const double *D, int32_t *tours, double *costs, int B, int n,
+                              int first_improvement, double *events, int32_t *n_events,
+                              int max_events, int32_t *status, int64_t *counters, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * guided_local_search — gnngls/algorithms.py:135-195, persistent on device, one CTA per
+ * instance, with the wall-clock test of :146 replaced by an explicit range of outer iterations
+ * so that callers can either run a fixed count or poll the clock between chunks.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gnngls_gls_args {
+    int32_t B, n;
+    const double *D;            /* [B,n,n]                                                        */
+    int32_t guide_kind;         /* gnngls_guide_kind                                              */
+    int32_t n_guides;           /* guide used in outer iteration it is guides[it % n_guides]      */
+    const void *guides;
+    int32_t *cur_tours;         /* [B,n+1] in: init_tour (or state when resume); out: current     */
+    double *cur_costs;          /* [B]     in: init_cost (or state);             out: current     */
+    int32_t *best_tours;        /* [B,n+1] out (in/out when resume)                               */
+    double *best_costs;         /* [B]     out (in/out when resume)                               */
+    double *k;                  /* [B] out when !resume (0.1*init_cost/n, :137), in when resume   */
+    int32_t *penalties;         /* [B,n,n] int32 in/out; may be NULL when !resume (not persisted) */
+    int32_t resume;             /* 0: zero penalties, run the initial local_search (:138-143)     */
+    int32_t iter_begin;         /* index of the first outer iteration of this call                */
+    int32_t n_iters;            /* number of outer iterations to run                              */
+    int32_t perturbation_moves;
+    int32_t first_improvement;
+    double *events;             /* [B,max_events] or NULL                                          */
+    int32_t *n_events;          /* [B] or NULL: total events of THIS call                         */
+    int32_t max_events;
+    int32_t *status;            /* [B] or NULL                                                    */
+    int64_t *counters;          /* [B,4] or NULL (see gnngls_local_search_batch)                  */
+} gnngls_gls_args;
+
+int gnngls_gls_batch(const gnngls_gls_args *args_host, void *stream);
+/* sizeof(gnngls_gls_args), for FFI bindings to verify their struct mirror */
+size_t gnngls_sizeof_gls_args(void);
+
+/* nearest_neighbor + tour_cost — gnngls/algorithms.py:9-18, gnngls/__init__.py:17-21 as used at
+ * scripts/test.py:85-90.  Greedy tour from `depot` on the guide (first minimum in ascending
+ * node id wins), then the sequential fp64 cost of that tour under D.
+ *   guide: guide_kind layout with n_guides == 1;  D may be NULL (then out_costs is not written) */
+int gnngls_nn_init_batch(int guide_kind, const void *guide, const double *D, int B, int n, int depot,
+                         int32_t *out_tours, double *out_costs, void *stream);
+
+/* gnngls/__init__.py:17-21 for a batch of tours. */
+int gnngls_tour_cost_batch(const double *D, const int32_t *tours, int B, int n, double *out_costs,
+                           void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Edge-regret model — gnngls/models.py:44-70 (+ dgl.nn.GATConv reached from models.py:23).
+ * Activations are fp32 row-major [M,128]; M = total line-graph nodes of the batch.
+ * ------------------------------------------------------------------------------------------- */
+#define GNNGLS_EMBED_DIM 128
+#define GNNGLS_HEADS 8
+#define GNNGLS_HEAD_DIM 16
+#define GNNGLS_HIDDEN_DIM 512
+
+/* input construction: datasets.py:14-20 + MinMaxScaler.transform (datasets.py:85) for line-graph
+ * node v = rank(i,j):  x0 = float(D[b,i,j]);  x1 = float(double(x0)*scale);  x = float(double(x1)+min_)
+ * (sklearn applies `X *= scale_; X += min_` in place on the float32 array with fp64 scalars: each
+ * step is evaluated in fp64 and rounded to fp32 — verified against sklearn in tests). */
+int gnngls_edge_features(const double *D, int B, int n, double scale, double min_, float *x, void *stream);
+
+/* embed_layer (models.py:57,66): h[M,128] = x[M,in_dim] * W[128,in_dim]^T + b */
+int gnngls_embed_forward(const float *x, int64_t M, int in_dim, const float *W, const float *b,
+                         float *h, int round_tf32, void *stream);
+
+/* dense implementation selector for the fc / feed-forward contractions */
+typedef enum gnngls_dense_impl {
+    GNNGLS_DENSE_TCGEN05 = 0,   /* TMA-fed tcgen05.mma kind::tf32, accumulators in TMEM (default) */
+    GNNGLS_DENSE_SIMT = 1       /* plain fp32 CUDA-core kernel: debug cross-check only            */
+} gnngls_dense_impl;
+
+/* GATConv.fc + attention scores (Appendix A of SURVEY.md):
+ *   ft[M,128] = h * Wfc[128,128]^T ; el[M,8] = sum_f ft*attn_l ; er[M,8] = sum_f ft*attn_r       */
+int gnngls_fc_forward(int impl, const float *h, int64_t M, const float *Wfc, const float *attn_l,
+                      const float *attn_r, float *ft, float *el, float *er, void *stream);
+
+/* Per-channel affine form of eval-mode BatchNorm1d: y = x*scale + shift
+ * (scale = gamma/sqrt(var+eps), shift = beta - mean*scale; models.py:27,35).
+ *
+ * round_tf32 (embed / aggregate): store the produced activations rounded to TF32 (cvt.rna), so
+ * that the tcgen05 kind::tf32 consumer — which ignores the low 13 mantissa bits of its operands —
+ * sees round-to-nearest instead of truncated inputs.  Pass 0 for the pure-fp32 debug path. */
+
+/* GAT aggregate over an arbitrary destination-sorted CSR graph + skip + BatchNorm1 (models.py:12-15,27):
+ *   h1[v] = BN1(h[v] + sum_u softmax_u(leaky_relu(el[u]+er[v])) ft[u] + gat_bias)               */
+int gnngls_gat_aggregate_csr(const int32_t *indptr, const int32_t *indices, int64_t M,
+                             const float *ft, const float *el, const float *er, const float *h,
+                             const float *gat_bias /* [128] or NULL */, const float *bn_scale,
+                             const float *bn_shift, float *h1, int round_tf32, void *stream);
+
+/* Same op for a batch of line graphs of K_n with the adjacency computed arithmetically
+ * (neighbours of (i,j) are (i,k) and (k,j)); M = B*n(n-1)/2.  `workspace` must hold
+ * gnngls_gat_kn_workspace_bytes(B,n) bytes. */
+size_t gnngls_gat_kn_workspace_bytes(int B, int n);
+int gnngls_gat_aggregate_kn(int B, int n, const float *ft, const float *el, const float *er,
+                            const float *h, const float *gat_bias, const float *bn_scale,
+                            const float *bn_shift, float *h1, int round_tf32, void *workspace,
+                            size_t workspace_bytes, void *stream);
+
+/* feed-forward block (models.py:28-35):
+ *   h_out = BN2(h1 + W2 * relu(W1 * h1 + b1) + b2),  W1[512,128], W2[128,512]
+ * `workspace` must hold gnngls_ff_workspace_bytes(impl, M) bytes (may be 0). */
+size_t gnngls_ff_workspace_bytes(int impl, int64_t M);
+int gnngls_ff_forward(int impl, const float *h1, int64_t M, const float *W1, const float *b1,
+                      const float *W2, const float *b2, const float *bn_scale, const float *bn_shift,
+                      float *h_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* decision_layer (models.py:63,69): y[M,out_dim] = h * Wd[out_dim,128]^T + bd */
+int gnngls_decision_forward(const float *h, int64_t M, int out_dim, const float *Wd, const float *bd,
+                            float *y, void *stream);
+
+/* scripts/test.py:79-83: MinMaxScaler.inverse_transform on the float32 array then clamp:
+ *   r1 = float(double(y) - min_);  r2 = float(double(r1) / scale);  regret = max(r2, 0)
+ * In place allowed. */
+int gnngls_regret_postprocess(const float *y, int64_t M, double scale, double min_, float *regret, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNGLS_B200_H_ */

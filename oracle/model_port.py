@@ -56,6 +56,8 @@ def kn_line_graph_edges(n):
 class EdgeListGraph:
     """Minimal stand-in for the DGLGraph surface the reference model touches."""
 
+    regular_degree = None
+
     def __init__(self, src, dst, num_nodes):
         self.src = torch.as_tensor(src, dtype=torch.int64)
         self.dst = torch.as_tensor(dst, dtype=torch.int64)
@@ -71,6 +73,7 @@ class EdgeListGraph:
             s = (s[None, :] + offs).reshape(-1)
             d = (d[None, :] + offs).reshape(-1)
         g = cls(s, d, N * batch)
+        g.regular_degree = 2 * (n - 2)      # dst-sorted, constant in-degree: enables the dense fast path
         g.ndata['e'] = torch.as_tensor(np.tile(kn_edge_list(n), (batch, 1)))
         return g
 
@@ -108,6 +111,15 @@ class GATConvPort(nn.Module):
         ft = self.fc(feat).view(N, H, F)
         el = (ft * self.attn_l).sum(-1)
         er = (ft * self.attn_r).sum(-1)
+        deg = getattr(graph, 'regular_degree', None)
+        if deg is not None:
+            # same formula on a dst-sorted constant-degree graph, without scatter ops (faster on CPU)
+            e = torch.nn.functional.leaky_relu(el[src].view(N, deg, H) + er[:, None, :], self._slope)
+            a = torch.softmax(e, dim=1)
+            out = torch.einsum('ndh,ndhf->nhf', a, ft[src].view(N, deg, H, F))
+            if self.bias is not None:
+                out = out + self.bias.view(1, H, F)
+            return out
         e = torch.nn.functional.leaky_relu(el[src] + er[dst], self._slope)      # [E,H]
         idx = dst[:, None].expand(-1, H)
         emax = torch.full((N, H), -math.inf, dtype=e.dtype).scatter_reduce(0, idx, e, 'amax')

@@ -1,0 +1,168 @@
+"""GPU parity of EdgePropertyPredictionModel (through the C ABI) against the reference's own
+models.py outputs (golden, fp64 yardstick) and the torch oracle.
+
+Tolerances (scaled regret output, |y| = O(1)):
+  fp32 path  (SIMT dense + CSR aggregate):  max|y - y64| <= 2e-4   (fp32 torch oracle itself: <5e-5)
+  TF32 paths (tcgen05 dense and/or mma.sync K_n aggregate): max|y - y64| <= 2e-2 and
+             <= 3e-3 against an oracle whose GEMM operands are rounded to TF32 the same way.
+"""
+import numpy as np
+import pytest
+import torch
+
+from gnngls_b200 import _ops, graph, instances, models
+from oracle import model_port
+from tests import _golden
+
+pytestmark = pytest.mark.gpu
+
+MODEL, TOP = _golden.load('model')
+TOL_FP32, TOL_TF32 = 2e-4, 2e-2
+
+
+def make_models(gat_bias=False):
+    torch.manual_seed(0)
+    port = model_port.EdgeModelPort(1, 128, 1, 3, n_heads=8, gat_bias=gat_bias)
+    model_port.randomize_bn_stats(port, seed=1)
+    if gat_bias:
+        for l in port.message_passing_layers:
+            torch.nn.init.normal_(l.message_passing.module.bias, std=0.1)
+    port.eval()
+    m = models.EdgePropertyPredictionModel(1, 128, 1, 3, n_heads=8)
+    m.load_state_dict(port.state_dict(), strict=True)
+    return port, m.cuda().eval()
+
+
+def run(m, n, B, x, dense, gat):
+    m.dense_impl, m.gat_impl = dense, gat
+    G = graph.LineGraph.complete(n, B, 'cuda')
+    with torch.no_grad():
+        return m(G, torch.as_tensor(x).cuda()).cpu().numpy()
+
+
+@pytest.mark.parametrize('dense,gat,tol', [('simt', 'csr', TOL_FP32), ('simt', 'kn', TOL_TF32),
+                                           ('tcgen05', 'csr', TOL_TF32), ('tcgen05', 'kn', TOL_TF32)])
+def test_model_matches_reference_golden(dense, gat, tol):
+    _, m = make_models()
+    for c in MODEL:
+        n, B = c.nB.tolist()
+        y = run(m, n, B, c.x, dense, gat)
+        err = np.abs(y - c.y64).max()
+        print(f'{dense}+{gat} n={n} B={B}: max|y-y64|={err:.3e} (|y|max={np.abs(c.y64).max():.3f})')
+        assert y.shape == c.y64.shape and np.isfinite(y).all()
+        assert err <= tol, (dense, gat, n, err)
+
+
+def test_paths_agree_and_batching_is_transparent():
+    port, m = make_models()
+    n, B = 12, 5
+    _, D = instances.random_instances(B, n, seed=4)
+    x = (instances.edge_features(D) / np.float32(np.sqrt(2))).reshape(-1, 1)
+    ref = run(m, n, B, x, 'simt', 'csr')
+    N = n * (n - 1) // 2
+    for b in range(B):          # batched == per-instance (eval-mode BN is per-node)
+        yb = run(m, n, 1, x[b * N:(b + 1) * N], 'simt', 'csr')
+        assert np.array_equal(yb, ref[b * N:(b + 1) * N])
+    assert np.abs(run(m, n, B, x, 'simt', 'kn') - ref).max() < TOL_TF32
+    assert np.abs(run(m, n, B, x, 'tcgen05', 'kn') - ref).max() < TOL_TF32
+    # arbitrary-CSR entry point (edge list in random order) == K_n graph
+    s, d = model_port.kn_line_graph_edges(n)
+    perm = np.random.default_rng(0).permutation(len(s))
+    g = graph.LineGraph.from_edges(s[perm], d[perm], N, device='cuda')
+    m.dense_impl, m.gat_impl = 'simt', 'auto'
+    with torch.no_grad():
+        y1 = m(g, torch.as_tensor(x[:N]).cuda()).cpu().numpy()
+    assert np.abs(y1 - ref[:N]).max() < 1e-5
+    with torch.no_grad():
+        y64 = port.double()(model_port.EdgeListGraph.kn_line_graph(n, B), torch.as_tensor(x).double()).numpy()
+    assert np.abs(ref - y64).max() < TOL_FP32
+
+
+def test_gat_bias_checkpoints():
+    port, m = make_models(gat_bias=True)
+    n, B = 9, 2
+    _, D = instances.random_instances(B, n, seed=5)
+    x = (instances.edge_features(D) / np.float32(np.sqrt(2))).reshape(-1, 1)
+    with torch.no_grad():
+        y64 = port.double()(model_port.EdgeListGraph.kn_line_graph(n, B), torch.as_tensor(x).double()).numpy()
+    assert np.abs(run(m, n, B, x, 'simt', 'csr') - y64).max() < TOL_FP32
+    assert np.abs(run(m, n, B, x, 'tcgen05', 'kn') - y64).max() < TOL_TF32
+
+
+def _tf32(t):
+    return models.tf32_round(t.float().contiguous()).double()
+
+
+def test_dense_kernels_against_tf32_rounded_oracle():
+    """fc / FF blocks alone: the tensor-core result must match an fp64 evaluation whose operands are
+    rounded to TF32 exactly as the kernels round them (tight), and the SIMT result the fp32 math."""
+    from gnngls_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(1)
+    for M in (1, 127, 128, 129, 1000, 4950 * 3 + 17):
+        h = torch.randn(M, 128)
+        W = torch.randn(128, 128) * 0.1
+        al, ar = torch.randn(128) * 0.3, torch.randn(128) * 0.3
+        W1, b1 = torch.randn(512, 128) * 0.1, torch.randn(512) * 0.1
+        W2, b2 = torch.randn(128, 512) * 0.05, torch.randn(128) * 0.1
+        sc, sh = torch.rand(128) + 0.5, torch.randn(128) * 0.1
+        p = _ops._ptr
+        for impl in (_ops.DENSE_SIMT, _ops.DENSE_TCGEN05):
+            tc = impl == _ops.DENSE_TCGEN05
+            hh = models.tf32_round(h) if tc else h
+            Wd = models.tf32_round(W) if tc else W
+            W1d, W2d = (models.tf32_round(W1), models.tf32_round(W2)) if tc else (W1, W2)
+            hd = hh.cuda()
+            ft = torch.empty(M, 128, device='cuda'); el = torch.empty(M, 8, device='cuda'); er = torch.empty(M, 8, device='cuda')
+            _lib.check(lib.gnngls_fc_forward(impl, p(hd), M, p(Wd.cuda()), p(al.cuda()), p(ar.cuda()), p(ft), p(el), p(er),
+                                             _ops._stream()))
+            ft64 = hh.double() @ Wd.double().t()
+            el64 = (ft64.view(M, 8, 16) * al.double().view(1, 8, 16)).sum(-1)
+            er64 = (ft64.view(M, 8, 16) * ar.double().view(1, 8, 16)).sum(-1)
+            tol = 2e-3 if tc else 1e-4         # tc: ft is stored TF32-rounded (|ft| ~ 1 -> 5e-4)
+            assert (ft.cpu().double() - ft64).abs().max() < tol, (M, impl)
+            assert (el.cpu().double() - el64).abs().max() < 1e-4 and (er.cpu().double() - er64).abs().max() < 1e-4
+            nbytes = lib.gnngls_ff_workspace_bytes(impl, M)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+            out = torch.empty(M, 128, device='cuda')
+            _lib.check(lib.gnngls_ff_forward(impl, p(hd), M, p(W1d.cuda()), p(b1.cuda()), p(W2d.cuda()), p(b2.cuda()),
+                                             p(sc.cuda()), p(sh.cuda()), p(out), p(ws), nbytes, _ops._stream()))
+            hid = torch.relu(hh.double() @ W1d.double().t() + b1.double())
+            if tc:
+                hid = _tf32(hid)
+            o64 = (hh.double() + hid @ W2d.double().t() + b2.double()) * sc.double() + sh.double()
+            assert (out.cpu().double() - o64).abs().max() < (3e-3 if tc else 2e-4), (M, impl)
+
+
+def test_glue_kernels_bit_exact():
+    from sklearn.preprocessing import MinMaxScaler
+    rng = np.random.default_rng(2)
+    B, n = 7, 23
+    _, D = instances.random_instances(B, n, seed=8)
+    fs = MinMaxScaler().fit(np.array([[0.003], [1.37]]))
+    rs = MinMaxScaler().fit(np.array([[0.0], [0.31]]))
+    x = _ops.edge_features(torch.as_tensor(D).cuda(), float(fs.scale_[0]), float(fs.min_[0])).cpu().numpy()
+    ref = fs.transform(instances.edge_features(D).reshape(-1, 1)).reshape(B, -1)
+    assert x.dtype == np.float32 and np.array_equal(x, ref)
+    y = (rng.random((B, n * (n - 1) // 2)).astype(np.float32) - np.float32(0.3))
+    r = _ops.regret_postprocess(torch.as_tensor(y).cuda(), float(rs.scale_[0]), float(rs.min_[0])).cpu().numpy()
+    ref = np.maximum(rs.inverse_transform(y.reshape(-1, 1).copy()), 0).reshape(B, -1)
+    assert np.array_equal(r, ref.astype(np.float32))
+
+
+def test_pipeline_tours_bit_exact_given_gpu_regrets():
+    """End to end (scripts/test.py:72-95): GPU regrets -> the CPU oracle's NN+GLS must produce exactly the GPU tours."""
+    from gnngls_b200 import pipeline
+    from oracle import gls_port
+    _, m = make_models()
+    n, B, K = 20, 24, 5
+    _, D = instances.random_instances(B, n, seed=6)
+    solver = pipeline.RegretGLS(m, micro_batch=7)
+    res = solver.solve(torch.as_tensor(D).cuda(), n_iters=K, perturbation_moves=20, keep_regret=True)
+    regret = res.regret.cpu().numpy()
+    assert regret.min() >= 0 and (regret > 0).any()
+    o_t, o_c = gls_port.pipeline_batch(D, regret, K, 20, nthreads=4)
+    assert np.array_equal(res.best_tours.cpu().numpy(), o_t)
+    assert np.array_equal(_golden.bits(res.best_costs.cpu().numpy()), _golden.bits(o_c))
+    t_h, c_h = solver.solve_host(D, chunk=10, n_iters=K, perturbation_moves=20)
+    assert np.array_equal(t_h, o_t) and np.array_equal(_golden.bits(c_h), _golden.bits(o_c))

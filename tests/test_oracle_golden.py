@@ -128,7 +128,7 @@ def test_model_port_reproduces_reference_outputs():
             y64 = m.double()(g, torch.from_numpy(c.x).double()).numpy()
             m.float()
         assert np.allclose(y64, c.y64, rtol=0, atol=1e-12)
-        assert np.allclose(y32, c.y32, rtol=0, atol=1e-5)
+        assert np.allclose(y32, c.y32, rtol=0, atol=1e-4)      # fp32 summation-order noise only
         # fp32 evaluation error vs the fp64 yardstick: the basis for the GPU tolerance
         assert np.abs(y32 - c.y64).max() < 5e-5
 
