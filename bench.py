@@ -124,13 +124,25 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_pass(port, D, n_iters, pm, threads):
+def cpu_calibrated_scalers(port, n):
+    """CPU twin of RegretGLS.calibrate_synthetic_regret_scaler (one calibration instance)."""
+    from gnngls_b200 import instances
+    from gnngls_b200.pipeline import Scalers
+    from oracle import model_port
+    s = Scalers()
+    _, D = instances.random_instances(1, n, seed=instances.DEFAULT_SEED - 1)
+    x = instances.edge_features(D)
+    x = ((x.astype(np.float64) * s.feat_scale).astype(np.float32).astype(np.float64) + s.feat_min).astype(np.float32)
+    with torch.no_grad():
+        y = port(model_port.EdgeListGraph.kn_line_graph(n, 1), torch.from_numpy(x[0]).reshape(-1, 1))
+    return s.calibrated(y)
+
+
+def cpu_reference_pass(port, D, n_iters, pm, threads, s):
     """The reference's test.py:72-95 flow on CPU via the oracle: torch-CPU model (all threads) then the
     C port of nearest_neighbor + guided_local_search across `threads` host threads."""
     from gnngls_b200 import instances
-    from gnngls_b200.pipeline import Scalers
     from oracle import gls_port, model_port
-    s = Scalers()
     B, n = D.shape[0], D.shape[-1]
     N = n * (n - 1) // 2
     x = instances.edge_features(D)
@@ -154,12 +166,13 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     port = make_port_model()
+    scalers = cpu_calibrated_scalers(port, args.n)
     _, D = instances.random_instances(args.ref_sample, args.n)
     for _ in range(args.warmup):
-        cpu_reference_pass(port, D, args.gls_iters, args.perturbation_moves, threads)
+        cpu_reference_pass(port, D, args.gls_iters, args.perturbation_moves, threads, scalers)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_pass(port, D, args.gls_iters, args.perturbation_moves, threads)
+        cpu_reference_pass(port, D, args.gls_iters, args.perturbation_moves, threads, scalers)
     dt = time.perf_counter() - t0
     value = args.ref_sample * args.steps / dt
     line = {
@@ -211,6 +224,11 @@ def main():
     _, D_np = instances.random_instances(S, n, seed=instances.DEFAULT_SEED + rank)
     D_host = torch.from_numpy(D_np).pin_memory()
     D_dev = D_host.to(dev)
+    if weights.startswith('random-init'):
+        # untrained weights give near-constant raw outputs: calibrate the synthetic regret scaler once so the
+        # guide is non-degenerate (a few % exact zeros, rest spread), identically on every rank
+        _, D_cal = instances.random_instances(min(S, args.micro_batch), n, seed=instances.DEFAULT_SEED - 1)
+        solver.calibrate_synthetic_regret_scaler(torch.from_numpy(D_cal).to(dev))
     kw = dict(n_iters=args.gls_iters, perturbation_moves=args.perturbation_moves)
     g_tours = torch.empty(world * S, n + 1, dtype=torch.int32, device=dev) if world > 1 else None
     g_costs = torch.empty(world * S, dtype=torch.float64, device=dev) if world > 1 else None
@@ -308,7 +326,8 @@ def main():
         port = make_port_model()
         sample = min(args.cpu_sample, S)
         t0 = time.perf_counter()
-        o_t, o_c = cpu_reference_pass(port, D_np[:sample], args.gls_iters, args.perturbation_moves, threads)
+        o_t, o_c = cpu_reference_pass(port, D_np[:sample], args.gls_iters, args.perturbation_moves, threads,
+                                      solver.scalers)
         dt = time.perf_counter() - t0
         cpu = {'value': sample / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': f'first {sample} instances of the same workload, {dt:.1f} s: oracle torch-CPU model + C port '

@@ -6,10 +6,12 @@
 //
 // Main path: one persistent, warp-specialised kernel template — TMA (cp.async.bulk.tensor, 128B
 // swizzle) feeds a 6-stage shared-memory ring, a single thread issues tcgen05.mma kind::tf32 with
-// fp32 accumulators in TMEM (double-buffered, 2 x 128 columns), four epilogue warps drain TMEM with
-// tcgen05.ld, transpose through shared memory and apply the fused epilogue with coalesced 128-bit
-// global accesses.  Operands are fp32 in memory; activations written by these epilogues are
-// rounded to TF32 (cvt.rna) so that the tensor core's operand truncation is exact.
+// fp32 accumulators in TMEM (double-buffered, 2 x 128 columns), eight epilogue warps drain TMEM with
+// tcgen05.ld (thread == output row) and apply the fused epilogue straight from registers with
+// 128-bit global accesses.  Operands are fp32 words in memory that already hold TF32-rounded values
+// (weights are rounded once on the host, activations by the producing kernel into a second
+// "_tf32" copy), so the tensor core's truncation of the low 13 mantissa bits is exact and the
+// residual stream itself stays in full fp32.
 //
 // Debug path (GNNGLS_DENSE_SIMT): plain fp32 CUDA-core GEMM with the same epilogues, used by the
 // tests to cross-check the tensor-core path.  Also here: embed_layer and decision_layer, which
@@ -29,12 +31,13 @@ enum { EPI_FC = 0, EPI_FF1 = 1, EPI_FF2 = 2 };
 struct EpiParams {
     int64_t M;
     float *out;          // FC: ft [M,128]; FF1: hid [M,512]; FF2: h_out [M,128]
+    float *out_tf32;     // FF2 only (nullable): copy of h_out rounded to TF32 for the next tensor-core GEMM
     float *el, *er;      // FC only, [M,8]
     const float *v0;     // FC: attn_l[128]; FF1: b1[512]; FF2: b2[128]
     const float *v1;     // FC: attn_r[128]; FF2: bn_scale[128]
     const float *v2;     // FF2: bn_shift[128]
-    const float *skip;   // FF2: h1 [M,128]
-    int round_tf32;      // round stored activations to TF32 (tensor-core path)
+    const float *skip;   // FF2: h1 [M,128] (fp32, unrounded)
+    int round_tf32;      // FF1: store the hidden activations rounded to TF32 (they only feed the next GEMM)
 };
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -42,9 +45,12 @@ __device__ __forceinline__ float tf32_rna(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+__device__ __forceinline__ float4 tf32_rna4(float4 v) {
+    return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+}
 
-// Fused epilogue for 4 consecutive columns [col, col+4) of one row.  Called with a full warp in
-// which lanes 4q..4q+3 hold consecutive column quads of the same row (needed by the FC reduction).
+// Fused epilogue for 4 consecutive columns [col, col+4) of one row (SIMT debug GEMM).  Called with a
+// full warp in which lanes 4q..4q+3 hold consecutive column quads of the same row (FC reduction).
 template <int EPI>
 __device__ __forceinline__ void epilogue_quad(const EpiParams &p, int64_t row, int col, float4 acc, bool valid) {
     if (EPI == EPI_FC) {
@@ -57,7 +63,6 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams &p, int64_t row, i
         sl += __shfl_xor_sync(0xffffffffu, sl, 2);
         sr += __shfl_xor_sync(0xffffffffu, sr, 2);
         if (valid) {
-            if (p.round_tf32) { acc.x = tf32_rna(acc.x); acc.y = tf32_rna(acc.y); acc.z = tf32_rna(acc.z); acc.w = tf32_rna(acc.w); }
             *reinterpret_cast<float4 *>(p.out + row * D_ + col) = acc;
             if ((col & 15) == 0) {   // first quad of a head: 16 columns per head
                 p.el[row * H_ + (col >> 4)] = sl;
@@ -70,7 +75,7 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams &p, int64_t row, i
         float4 o;
         o.x = fmaxf(acc.x + b.x, 0.f); o.y = fmaxf(acc.y + b.y, 0.f);
         o.z = fmaxf(acc.z + b.z, 0.f); o.w = fmaxf(acc.w + b.w, 0.f);
-        if (p.round_tf32) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
+        if (p.round_tf32) o = tf32_rna4(o);
         *reinterpret_cast<float4 *>(p.out + row * HID_ + col) = o;
     } else {
         if (!valid) return;
@@ -81,8 +86,59 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams &p, int64_t row, i
         float4 o;
         o.x = (s.x + (acc.x + b.x)) * sc.x + sh.x; o.y = (s.y + (acc.y + b.y)) * sc.y + sh.y;
         o.z = (s.z + (acc.z + b.z)) * sc.z + sh.z; o.w = (s.w + (acc.w + b.w)) * sc.w + sh.w;
-        if (p.round_tf32) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
         *reinterpret_cast<float4 *>(p.out + row * D_ + col) = o;
+        if (p.out_tf32) *reinterpret_cast<float4 *>(p.out_tf32 + row * D_ + col) = tf32_rna4(o);
+    }
+}
+
+// Thread-per-row epilogue of the tensor-core GEMM: this thread owns 32 consecutive accumulator
+// columns [col, col+32) of `row` (straight out of tcgen05.ld), `sv` are the per-column vectors
+// staged in shared memory (FC: attn_l|attn_r; FF1: b1; FF2: b2|bn_scale|bn_shift).
+template <int EPI>
+__device__ __forceinline__ void epilogue_row32(const EpiParams &p, const float *sv, int64_t row, int col, float (&v)[32]) {
+    if (EPI == EPI_FC) {
+        float sl[2] = {0.f, 0.f}, sr[2] = {0.f, 0.f};       // 32 columns = two heads of 16
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 al = *reinterpret_cast<const float4 *>(sv + col + 4 * j);
+            const float4 ar = *reinterpret_cast<const float4 *>(sv + D_ + col + 4 * j);
+            sl[j >> 2] += v[4 * j] * al.x + v[4 * j + 1] * al.y + v[4 * j + 2] * al.z + v[4 * j + 3] * al.w;
+            sr[j >> 2] += v[4 * j] * ar.x + v[4 * j + 1] * ar.y + v[4 * j + 2] * ar.z + v[4 * j + 3] * ar.w;
+        }
+        float *o = p.out + row * D_ + col;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4 *>(o + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        *reinterpret_cast<float2 *>(p.el + row * H_ + (col >> 4)) = make_float2(sl[0], sl[1]);
+        *reinterpret_cast<float2 *>(p.er + row * H_ + (col >> 4)) = make_float2(sr[0], sr[1]);
+    } else if (EPI == EPI_FF1) {
+        float *o = p.out + row * HID_ + col;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b = *reinterpret_cast<const float4 *>(sv + col + 4 * j);
+            float4 r;
+            r.x = fmaxf(v[4 * j] + b.x, 0.f); r.y = fmaxf(v[4 * j + 1] + b.y, 0.f);
+            r.z = fmaxf(v[4 * j + 2] + b.z, 0.f); r.w = fmaxf(v[4 * j + 3] + b.w, 0.f);
+            if (p.round_tf32) r = tf32_rna4(r);
+            *reinterpret_cast<float4 *>(o + 4 * j) = r;
+        }
+    } else {
+        const float *sk = p.skip + row * D_ + col;
+        float4 s[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = *reinterpret_cast<const float4 *>(sk + 4 * j);
+        float *o = p.out + row * D_ + col;
+        float *ot = p.out_tf32 ? p.out_tf32 + row * D_ + col : nullptr;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b = *reinterpret_cast<const float4 *>(sv + col + 4 * j);
+            const float4 sc = *reinterpret_cast<const float4 *>(sv + D_ + col + 4 * j);
+            const float4 sh = *reinterpret_cast<const float4 *>(sv + 2 * D_ + col + 4 * j);
+            float4 r;
+            r.x = (s[j].x + (v[4 * j] + b.x)) * sc.x + sh.x; r.y = (s[j].y + (v[4 * j + 1] + b.y)) * sc.y + sh.y;
+            r.z = (s[j].z + (v[4 * j + 2] + b.z)) * sc.z + sh.z; r.w = (s[j].w + (v[4 * j + 3] + b.w)) * sc.w + sh.w;
+            *reinterpret_cast<float4 *>(o + 4 * j) = r;
+            if (ot) *reinterpret_cast<float4 *>(ot + 4 * j) = tf32_rna4(r);
+        }
     }
 }
 
@@ -189,11 +245,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 constexpr int BM = 128, BN = 128, BK = 32;           // BK fp32 = 128 bytes = one swizzle row
 constexpr int STAGES = 6;
 constexpr int STAGE_BYTES = (BM + BN) * BK * 4;      // 32 KB
-constexpr int STG_LD = 36;                           // staging row stride (floats): conflict-free quarter-warps
-constexpr int STG_BYTES_PER_WARP = 32 * STG_LD * 4;
-constexpr int GEMM_THREADS = 192;                    // warp0 TMA, warp1 MMA/TMEM, warps 2..5 epilogue
+constexpr int EPI_WARPS = 8;                         // two per TMEM lane quarter, 64 columns each
+constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;   // warp0 TMA, warp1 MMA/TMEM, warps 2..9 epilogue
 constexpr int TMEM_COLS = 256;                       // two 128-column fp32 accumulators
-constexpr size_t GEMM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP + 256;
+constexpr int SVEC_FLOATS = 512;                     // per-column epilogue vectors staged in smem
+constexpr size_t GEMM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + SVEC_FLOATS * 4 + 256;
 
 template <int N_TOTAL, int K_TOTAL, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -203,8 +259,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char *stage_base = smem;
-    float *staging = reinterpret_cast<float *>(smem + (size_t)STAGES * STAGE_BYTES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP);
+    float *svec = reinterpret_cast<float *>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES + SVEC_FLOATS * 4);
     uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
 
@@ -212,11 +268,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int64_t m_tiles = (p.M + BM - 1) / BM;
     const int64_t n_work = m_tiles * NB;
 
+    // per-column epilogue vectors -> shared memory
+    if (EPI == EPI_FC) {
+        for (int c = threadIdx.x; c < D_; c += GEMM_THREADS) { svec[c] = p.v0[c]; svec[D_ + c] = p.v1[c]; }
+    } else if (EPI == EPI_FF1) {
+        for (int c = threadIdx.x; c < HID_; c += GEMM_THREADS) svec[c] = p.v0[c];
+    } else {
+        for (int c = threadIdx.x; c < D_; c += GEMM_THREADS) { svec[c] = p.v0[c]; svec[D_ + c] = p.v1[c]; svec[2 * D_ + c] = p.v2[c]; }
+    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -270,31 +334,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else {
         // ------------------------------------------------------------------ epilogue warps
         const int q = warp & 3;                               // TMEM lane quarter this warp may access
-        float *stg = staging + (size_t)(warp - 2) * 32 * STG_LD;
+        const int half = (warp - 2) >> 2;                     // which 64 accumulator columns
         uint32_t acc = 0, acc_phase = 0;
         for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int m_blk = (int)(w / NB), n_blk = (int)(w % NB);
+            const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < 2; ++c) {
+                const int col_in_tile = half * 64 + c * 32;
                 float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)                   // thread == row: 8 x float4 into its staging row
-                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                __syncwarp();
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {              // 4 rows per pass, 8 lanes (x float4) per row
-                    const int r = it * 4 + (lane >> 3);
-                    const float4 a4 = *reinterpret_cast<const float4 *>(stg + r * STG_LD + 4 * (lane & 7));
-                    const int64_t row = (int64_t)m_blk * BM + q * 32 + r;
-                    const int col = n_blk * BN + c * 32 + 4 * (lane & 7);
-                    epilogue_quad<EPI>(p, row, col, a4, row < p.M);
-                }
-                __syncwarp();
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + col_in_tile, v);
+                if (row < p.M) epilogue_row32<EPI>(p, svec, row, n_blk * BN + col_in_tile, v);
             }
             tc_fence_before();
+            __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -409,7 +464,7 @@ int launch_simt_gemm(const float *A, const float *W, const EpiParams &p, cudaStr
 // embed_layer / decision_layer
 // ================================================================================================
 __global__ void embed_kernel(const float *__restrict__ x, int64_t M, int in_dim, const float *__restrict__ W,
-                             const float *__restrict__ b, float *__restrict__ h, int round_tf32) {
+                             const float *__restrict__ b, float *__restrict__ h, float *__restrict__ h_tf32) {
     // one warp per node, lane owns 4 output channels
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -423,8 +478,8 @@ __global__ void embed_kernel(const float *__restrict__ x, int64_t M, int in_dim,
             o.z = fmaf(xv, W[(4 * lane + 2) * in_dim + k], o.z);
             o.w = fmaf(xv, W[(4 * lane + 3) * in_dim + k], o.w);
         }
-        if (round_tf32) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
         *reinterpret_cast<float4 *>(h + m * D_ + 4 * lane) = o;
+        if (h_tf32) *reinterpret_cast<float4 *>(h_tf32 + m * D_ + 4 * lane) = tf32_rna4(o);
     }
 }
 
@@ -454,11 +509,11 @@ int elementwise_grid(int64_t warps_needed, int threads) {
 }  // namespace
 
 extern "C" int gnngls_embed_forward(const float *x, int64_t M, int in_dim, const float *W, const float *b, float *h,
-                                    int round_tf32, void *stream) {
+                                    float *h_tf32, void *stream) {
     GNNGLS_REQUIRE(x && W && b && h, GNNGLS_ERR_BAD_ARG, "null pointer argument");
     GNNGLS_REQUIRE(in_dim >= 1, GNNGLS_ERR_BAD_ARG, "in_dim must be >= 1");
     if (M <= 0) return GNNGLS_OK;
-    embed_kernel<<<elementwise_grid(M, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, M, in_dim, W, b, h, round_tf32);
+    embed_kernel<<<elementwise_grid(M, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, M, in_dim, W, b, h, h_tf32);
     GNNGLS_LAUNCH_OK("embed_kernel");
     return GNNGLS_OK;
 }
@@ -480,8 +535,8 @@ extern "C" int gnngls_fc_forward(int impl, const float *h, int64_t M, const floa
     EpiParams p{};
     p.M = M; p.out = ft; p.el = el; p.er = er; p.v0 = attn_l; p.v1 = attn_r;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (impl == GNNGLS_DENSE_TCGEN05) { p.round_tf32 = 1; return launch_tc_gemm<D_, D_, EPI_FC>(h, Wfc, p, st); }
-    if (impl == GNNGLS_DENSE_SIMT) { p.round_tf32 = 0; return launch_simt_gemm<D_, D_, EPI_FC>(h, Wfc, p, st); }
+    if (impl == GNNGLS_DENSE_TCGEN05) return launch_tc_gemm<D_, D_, EPI_FC>(h, Wfc, p, st);
+    if (impl == GNNGLS_DENSE_SIMT) return launch_simt_gemm<D_, D_, EPI_FC>(h, Wfc, p, st);
     GNNGLS_REQUIRE(false, GNNGLS_ERR_BAD_ARG, "unknown dense impl %d", impl);
 }
 
@@ -490,9 +545,10 @@ extern "C" size_t gnngls_ff_workspace_bytes(int impl, int64_t M) {
     return M > 0 ? (size_t)M * HID_ * sizeof(float) : 0;     // hidden activations [M,512]
 }
 
-extern "C" int gnngls_ff_forward(int impl, const float *h1, int64_t M, const float *W1, const float *b1,
-                                 const float *W2, const float *b2, const float *bn_scale, const float *bn_shift,
-                                 float *h_out, void *workspace, size_t workspace_bytes, void *stream) {
+extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32, int64_t M, const float *W1,
+                                 const float *b1, const float *W2, const float *b2, const float *bn_scale,
+                                 const float *bn_shift, float *h_out, float *h_out_tf32, void *workspace,
+                                 size_t workspace_bytes, void *stream) {
     GNNGLS_REQUIRE(h1 && W1 && b1 && W2 && b2 && bn_scale && bn_shift && h_out, GNNGLS_ERR_BAD_ARG, "null pointer argument");
     if (M <= 0) return GNNGLS_OK;
     GNNGLS_REQUIRE(workspace && workspace_bytes >= gnngls_ff_workspace_bytes(impl, M), GNNGLS_ERR_WORKSPACE,
@@ -502,14 +558,15 @@ extern "C" int gnngls_ff_forward(int impl, const float *h1, int64_t M, const flo
     EpiParams p1{};
     p1.M = M; p1.out = hid; p1.v0 = b1;
     EpiParams p2{};
-    p2.M = M; p2.out = h_out; p2.v0 = b2; p2.v1 = bn_scale; p2.v2 = bn_shift; p2.skip = h1;
+    p2.M = M; p2.out = h_out; p2.out_tf32 = h_out_tf32; p2.v0 = b2; p2.v1 = bn_scale; p2.v2 = bn_shift; p2.skip = h1;
+    const float *a1 = h1_tf32 ? h1_tf32 : h1;                 // GEMM operand; the skip path always reads fp32 h1
     if (impl == GNNGLS_DENSE_TCGEN05) {
-        p1.round_tf32 = p2.round_tf32 = 1;
-        if (int rc = launch_tc_gemm<HID_, D_, EPI_FF1>(h1, W1, p1, st)) return rc;
+        p1.round_tf32 = 1;
+        if (int rc = launch_tc_gemm<HID_, D_, EPI_FF1>(a1, W1, p1, st)) return rc;
         return launch_tc_gemm<D_, HID_, EPI_FF2>(hid, W2, p2, st);
     }
     if (impl == GNNGLS_DENSE_SIMT) {
-        if (int rc = launch_simt_gemm<HID_, D_, EPI_FF1>(h1, W1, p1, st)) return rc;
+        if (int rc = launch_simt_gemm<HID_, D_, EPI_FF1>(a1, W1, p1, st)) return rc;
         return launch_simt_gemm<D_, HID_, EPI_FF2>(hid, W2, p2, st);
     }
     GNNGLS_REQUIRE(false, GNNGLS_ERR_BAD_ARG, "unknown dense impl %d", impl);

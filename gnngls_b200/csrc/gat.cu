@@ -14,8 +14,9 @@
 //    that vertex's star (n-1 rows) in shared memory ONCE and produces, for all n-1 destinations
 //    that contain the vertex, the partial numerator/denominator/max of their softmax with
 //    mma.sync TF32 (attention weights are generated directly in the A-fragment registers,
-//    flash-attention style).  A combine kernel merges the two partials of each destination and
-//    applies skip + BatchNorm.  Every ft row is read from L2/HBM exactly twice per layer.
+//    flash-attention style).  Each destination belongs to two stars: the CTA that finishes second
+//    (arrival counter) merges the two partials and applies bias + skip + BatchNorm in its own
+//    epilogue.  Every ft row is read from L2/HBM exactly twice per layer.
 #include <cstdint>
 #include <cmath>
 #include "common.h"
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(CSR_WARPS * 32)
 gat_csr_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, int64_t M,
                const float *__restrict__ ft, const float *__restrict__ el, const float *__restrict__ er,
                const float *__restrict__ h, const float *__restrict__ bias, const float *__restrict__ bn_scale,
-               const float *__restrict__ bn_shift, float *__restrict__ h1, int round_tf32) {
+               const float *__restrict__ bn_shift, float *__restrict__ h1, float *__restrict__ h1_tf32) {
     __shared__ __align__(16) float ps[CSR_WARPS][32][H_];   // edge-tile weights
     __shared__ int us[CSR_WARPS][32];                      // edge-tile sources
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hh = lane >> 2;
@@ -141,8 +142,8 @@ gat_csr_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, 
         float4 o;
         o.x = (hv.x + g.x) * sc.x + sh.x; o.y = (hv.y + g.y) * sc.y + sh.y;
         o.z = (hv.z + g.z) * sc.z + sh.z; o.w = (hv.w + g.w) * sc.w + sh.w;
-        if (round_tf32) o = tf32_round4(o);
         *reinterpret_cast<float4 *>(h1 + v * D_ + 4 * lane) = o;
+        if (h1_tf32) *reinterpret_cast<float4 *>(h1_tf32 + v * D_ + 4 * lane) = tf32_round4(o);
     }
 }
 
@@ -181,9 +182,132 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&
 
 // Partials, indexed [(b*n + i)*n + j] for star vertex i and destination {i,j}:
 //   pnum[.,128]: sum_k w*ft   pden[.,8]: sum_k w   pmax[.,8]: log2-scaled max used for w
-__global__ void __launch_bounds__(STAR_THREADS)
+struct StarCtx {
+    int n, i, b, hd, g, t;
+    float m1, m2;
+    int a1;
+    const float *Fh;      // star features, offset to this warp's head
+    const float *ELs, *ERs;
+    int ksteps;
+    float *pnum, *pden, *pmax;
+    int *arrive;          // [B*N*8] arrival counters (zeroed per launch)
+    const float *h, *bias, *bn_scale, *bn_shift;
+    float *h1, *h1_tf32;
+};
+
+// Finish one destination row for this warp's head.  The quad (4 lanes sharing g) owns the row:
+// lane t holds features {2t,2t+1} and {8+2t,9+2t} of the head.  Protocol (both stars of a
+// destination run it): publish my partial -> __threadfence -> bump the arrival counter; whoever
+// arrives second reads the other partial (L2, .cg), merges flash-style and applies
+// bias + skip + BatchNorm1.  No separate combine kernel, one partial read per destination.
+__device__ __forceinline__ void finish_row(const StarCtx &c, int j, float2 n0, float2 n1, float den, float mx) {
+    const bool live = (j < c.n) && (j != c.i);          // uniform across the quad
+    const int64_t mine = ((int64_t)c.b * c.n + c.i) * c.n + j;
+    if (live) {
+        float *o = c.pnum + mine * D_ + c.hd * 16 + 2 * c.t;
+        __stcg(reinterpret_cast<float2 *>(o), n0);
+        __stcg(reinterpret_cast<float2 *>(o + 8), n1);
+        if (c.t == 0) { __stcg(c.pden + mine * H_ + c.hd, den); __stcg(c.pmax + mine * H_ + c.hd, mx); }
+    }
+    __threadfence();
+    __syncwarp();
+    const int64_t N = (int64_t)c.n * (c.n - 1) / 2;
+    const int64_t v = live ? (int64_t)c.b * N + kn_node(c.i, j, c.n) : 0;
+    int ticket = 0;
+    if (live && c.t == 0) ticket = atomicAdd(c.arrive + v * H_ + c.hd, 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, (threadIdx.x & 31) & ~3);
+    if (!live || ticket == 0) return;                   // first to arrive: the other star finishes the row
+    __threadfence();
+    const int64_t other = ((int64_t)c.b * c.n + j) * c.n + c.i;
+    const float *po = c.pnum + other * D_ + c.hd * 16 + 2 * c.t;
+    const float2 q0 = __ldcg(reinterpret_cast<const float2 *>(po));
+    const float2 q1 = __ldcg(reinterpret_cast<const float2 *>(po + 8));
+    const float d2 = __ldcg(c.pden + other * H_ + c.hd), x2 = __ldcg(c.pmax + other * H_ + c.hd);
+    const float m = fmaxf(mx, x2);
+    const float s1 = ex2(mx - m), s2 = ex2(x2 - m);
+    const float inv = 1.f / fmaf(den, s1, d2 * s2);
+    const float a1 = s1 * inv, a2 = s2 * inv;
+    const int f0 = c.hd * 16 + 2 * c.t;
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+        const int f = f0 + 8 * part;
+        const float2 mine2 = part ? n1 : n0, oth2 = part ? q1 : q0;
+        const float2 hv = *reinterpret_cast<const float2 *>(c.h + v * D_ + f);
+        const float2 sc = *reinterpret_cast<const float2 *>(c.bn_scale + f);
+        const float2 sh = *reinterpret_cast<const float2 *>(c.bn_shift + f);
+        float2 bb = make_float2(0.f, 0.f);
+        if (c.bias) bb = *reinterpret_cast<const float2 *>(c.bias + f);
+        float2 r;
+        r.x = (hv.x + (fmaf(mine2.x, a1, oth2.x * a2) + bb.x)) * sc.x + sh.x;
+        r.y = (hv.y + (fmaf(mine2.y, a1, oth2.y * a2) + bb.y)) * sc.y + sh.y;
+        *reinterpret_cast<float2 *>(c.h1 + v * D_ + f) = r;
+        if (c.h1_tf32)
+            *reinterpret_cast<float2 *>(c.h1_tf32 + v * D_ + f) =
+                make_float2(__uint_as_float(tf32_bits(r.x)), __uint_as_float(tf32_bits(r.y)));
+    }
+}
+
+// NT m-tiles (16 destinations each) processed together so that el and the B fragments of a k-step
+// are loaded once for NT tiles.  Per attention weight: FADD + FFMA + FMNMX + MUFU.EX2; the weights
+// go to the tensor core as raw fp32 bits (hardware keeps the top 19 bits) and the softmax
+// denominator comes from a third MMA against a ones fragment, so numerator and denominator see
+// identically truncated weights.
+template <int NT>
+__device__ __forceinline__ void star_tiles(const StarCtx &c, int mt0) {
+    float c1a[NT][2], c2a[NT][2], mxa[NT][2];           // per tile, rows (lo,hi): er-mx, 0.2*er-mx, mx
+    float acc0[NT][4], acc1[NT][4], accs[NT][4];
+#pragma unroll
+    for (int u = 0; u < NT; ++u) {
+        const int j_lo = (mt0 + u) * 16 + c.g, j_hi = j_lo + 8;
+        const float er_lo = c.ERs[j_lo * H_ + c.hd], er_hi = c.ERs[j_hi * H_ + c.hd];
+        mxa[u][0] = lrelu(((c.a1 == j_lo) ? c.m2 : c.m1) + er_lo);
+        mxa[u][1] = lrelu(((c.a1 == j_hi) ? c.m2 : c.m1) + er_hi);
+        c1a[u][0] = er_lo - mxa[u][0]; c2a[u][0] = kSlope * er_lo - mxa[u][0];
+        c1a[u][1] = er_hi - mxa[u][1]; c2a[u][1] = kSlope * er_hi - mxa[u][1];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { acc0[u][q] = 0.f; acc1[u][q] = 0.f; accs[u][q] = 0.f; }
+    }
+    const uint32_t one = __float_as_uint(1.0f);
+    for (int ks = 0; ks < c.ksteps; ++ks) {
+        const int k_lo = ks * 8 + c.t, k_hi = k_lo + 4;
+        const float el_lo = c.ELs[k_lo * H_ + c.hd], el_hi = c.ELs[k_hi * H_ + c.hd];
+        const float *r_lo = c.Fh + (size_t)k_lo * FS_LD + c.g, *r_hi = c.Fh + (size_t)k_hi * FS_LD + c.g;
+        const uint32_t b00 = __float_as_uint(r_lo[0]), b01 = __float_as_uint(r_hi[0]);
+        const uint32_t b10 = __float_as_uint(r_lo[8]), b11 = __float_as_uint(r_hi[8]);
+#pragma unroll
+        for (int u = 0; u < NT; ++u) {
+            // leaky_relu(el+er) - mx == max(el + (er-mx), 0.2*el + (0.2*er-mx))
+            float w0 = ex2(fmaxf(el_lo + c1a[u][0], fmaf(kSlope, el_lo, c2a[u][0])));   // (row lo, col k_lo)
+            float w1 = ex2(fmaxf(el_lo + c1a[u][1], fmaf(kSlope, el_lo, c2a[u][1])));   // (row hi, col k_lo)
+            float w2 = ex2(fmaxf(el_hi + c1a[u][0], fmaf(kSlope, el_hi, c2a[u][0])));   // (row lo, col k_hi)
+            float w3 = ex2(fmaxf(el_hi + c1a[u][1], fmaf(kSlope, el_hi, c2a[u][1])));   // (row hi, col k_hi)
+            if ((ks >> 1) == mt0 + u) {                  // tile touches the diagonal: a node is not its own neighbour
+                const int j_lo = (mt0 + u) * 16 + c.g, j_hi = j_lo + 8;
+                if (k_lo == j_lo) w0 = 0.f;
+                if (k_lo == j_hi) w1 = 0.f;
+                if (k_hi == j_lo) w2 = 0.f;
+                if (k_hi == j_hi) w3 = 0.f;
+            }
+            const uint32_t a[4] = {__float_as_uint(w0), __float_as_uint(w1), __float_as_uint(w2), __float_as_uint(w3)};
+            mma_tf32_16x8x8(acc0[u], a, b00, b01);
+            mma_tf32_16x8x8(acc1[u], a, b10, b11);
+            mma_tf32_16x8x8(accs[u], a, one, one);       // row sums of the (truncated) weights
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NT; ++u) {
+        const int j_lo = (mt0 + u) * 16 + c.g;
+        finish_row(c, j_lo, make_float2(acc0[u][0], acc0[u][1]), make_float2(acc1[u][0], acc1[u][1]), accs[u][0], mxa[u][0]);
+        finish_row(c, j_lo + 8, make_float2(acc0[u][2], acc0[u][3]), make_float2(acc1[u][2], acc1[u][3]), accs[u][2], mxa[u][1]);
+    }
+}
+
+__global__ void __launch_bounds__(STAR_THREADS, 3)
 gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict__ el, const float *__restrict__ er,
-                   float *__restrict__ pnum, float *__restrict__ pden, float *__restrict__ pmax) {
+                   float *__restrict__ pnum, float *__restrict__ pden, float *__restrict__ pmax,
+                   int *__restrict__ arrive, const float *__restrict__ h, const float *__restrict__ bias,
+                   const float *__restrict__ bn_scale, const float *__restrict__ bn_shift, float *__restrict__ h1,
+                   float *__restrict__ h1_tf32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int KP = round_up(n, 8), MP = round_up(n, 16);
     float *Fs = reinterpret_cast<float *>(smem_raw);          // [KP][FS_LD] tf32-rounded ft rows of the star
@@ -237,100 +361,23 @@ gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict_
     __syncthreads();
 
     // ---- main loop: warp <-> head; m-tiles of 16 destinations, k-steps of 8 star members
-    const int hd = warp;
-    const int g = lane >> 2, t = lane & 3;
-    const float m1 = TM1[hd], m2 = TM2[hd];
-    const int a1 = TA1[hd];
-    const float *Fh = Fs + hd * 16;
-    const int ksteps = KP / 8;
-    for (int mt = 0; mt < MP / 16; ++mt) {
-        const int j_lo = mt * 16 + g, j_hi = j_lo + 8;
-        const float er_lo = ERs[j_lo * H_ + hd], er_hi = ERs[j_hi * H_ + hd];
-        // softmax shift of this partial: leaky_relu is monotone, so the max score over the star
-        // minus the destination itself is leaky_relu(max_k el + er)
-        const float mx_lo = lrelu(((a1 == j_lo) ? m2 : m1) + er_lo);
-        const float mx_hi = lrelu(((a1 == j_hi) ? m2 : m1) + er_hi);
-        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-        float sum_lo = 0.f, sum_hi = 0.f;
-        for (int ks = 0; ks < ksteps; ++ks) {
-            const int k_lo = ks * 8 + t, k_hi = k_lo + 4;
-            const float el_lo = ELs[k_lo * H_ + hd], el_hi = ELs[k_hi * H_ + hd];
-            float w0 = ex2(lrelu(el_lo + er_lo) - mx_lo);   // (row j_lo, col k_lo)
-            float w1 = ex2(lrelu(el_lo + er_hi) - mx_hi);   // (row j_hi, col k_lo)
-            float w2 = ex2(lrelu(el_hi + er_lo) - mx_lo);   // (row j_lo, col k_hi)
-            float w3 = ex2(lrelu(el_hi + er_hi) - mx_hi);   // (row j_hi, col k_hi)
-            if ((ks >> 1) == mt) {                          // tile touches the diagonal: a node is not its own neighbour
-                if (k_lo == j_lo) w0 = 0.f;
-                if (k_lo == j_hi) w1 = 0.f;
-                if (k_hi == j_lo) w2 = 0.f;
-                if (k_hi == j_hi) w3 = 0.f;
-            }
-            uint32_t a[4];
-            a[0] = tf32_bits(w0); a[1] = tf32_bits(w1); a[2] = tf32_bits(w2); a[3] = tf32_bits(w3);
-            sum_lo += __uint_as_float(a[0]) + __uint_as_float(a[2]);
-            sum_hi += __uint_as_float(a[1]) + __uint_as_float(a[3]);
-            const float *r_lo = Fh + (size_t)k_lo * FS_LD + g, *r_hi = Fh + (size_t)k_hi * FS_LD + g;
-            mma_tf32_16x8x8(c0, a, __float_as_uint(r_lo[0]), __float_as_uint(r_hi[0]));
-            mma_tf32_16x8x8(c1, a, __float_as_uint(r_lo[8]), __float_as_uint(r_hi[8]));
-        }
-        sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
-        sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
-        const int64_t prow = ((int64_t)b * n + i) * n;
-        if (j_lo < n && j_lo != i) {
-            float *o = pnum + (prow + j_lo) * D_ + hd * 16 + 2 * t;
-            *reinterpret_cast<float2 *>(o) = make_float2(c0[0], c0[1]);
-            *reinterpret_cast<float2 *>(o + 8) = make_float2(c1[0], c1[1]);
-            if (t == 0) { pden[(prow + j_lo) * H_ + hd] = sum_lo; pmax[(prow + j_lo) * H_ + hd] = mx_lo; }
-        }
-        if (j_hi < n && j_hi != i) {
-            float *o = pnum + (prow + j_hi) * D_ + hd * 16 + 2 * t;
-            *reinterpret_cast<float2 *>(o) = make_float2(c0[2], c0[3]);
-            *reinterpret_cast<float2 *>(o + 8) = make_float2(c1[2], c1[3]);
-            if (t == 0) { pden[(prow + j_hi) * H_ + hd] = sum_hi; pmax[(prow + j_hi) * H_ + hd] = mx_hi; }
-        }
-    }
-}
-
-// merge the two partials of destination {i,j} (flash-style rescale), add bias + skip, BatchNorm1
-__global__ void __launch_bounds__(128)
-gat_kn_combine_kernel(int n, const float *__restrict__ pnum, const float *__restrict__ pden,
-                      const float *__restrict__ pmax, const float *__restrict__ h, const float *__restrict__ bias,
-                      const float *__restrict__ bn_scale, const float *__restrict__ bn_shift, float *__restrict__ h1,
-                      int round_tf32) {
-    const int b = blockIdx.x / n, i = blockIdx.x - b * n;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hh = lane >> 2;
-    const int64_t N = (int64_t)n * (n - 1) / 2;
-    const float4 sc = *reinterpret_cast<const float4 *>(bn_scale + 4 * lane);
-    const float4 sh = *reinterpret_cast<const float4 *>(bn_shift + 4 * lane);
-    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias) bb = *reinterpret_cast<const float4 *>(bias + 4 * lane);
-    for (int j = i + 1 + warp; j < n; j += 4) {
-        const int64_t p1 = ((int64_t)b * n + i) * n + j, p2 = ((int64_t)b * n + j) * n + i;
-        const int64_t v = (int64_t)b * N + kn_node(i, j, n);
-        const float4 n1 = *reinterpret_cast<const float4 *>(pnum + p1 * D_ + 4 * lane);
-        const float4 n2 = *reinterpret_cast<const float4 *>(pnum + p2 * D_ + 4 * lane);
-        const float x1 = pmax[p1 * H_ + hh], x2 = pmax[p2 * H_ + hh];
-        const float d1 = pden[p1 * H_ + hh], d2 = pden[p2 * H_ + hh];
-        const float mx = fmaxf(x1, x2);
-        const float s1 = ex2(x1 - mx), s2 = ex2(x2 - mx);
-        const float inv = 1.f / fmaf(d1, s1, d2 * s2);
-        const float a1 = s1 * inv, a2 = s2 * inv;
-        const float4 hv = *reinterpret_cast<const float4 *>(h + v * D_ + 4 * lane);
-        float4 o;
-        o.x = (hv.x + (fmaf(n1.x, a1, n2.x * a2) + bb.x)) * sc.x + sh.x;
-        o.y = (hv.y + (fmaf(n1.y, a1, n2.y * a2) + bb.y)) * sc.y + sh.y;
-        o.z = (hv.z + (fmaf(n1.z, a1, n2.z * a2) + bb.z)) * sc.z + sh.z;
-        o.w = (hv.w + (fmaf(n1.w, a1, n2.w * a2) + bb.w)) * sc.w + sh.w;
-        if (round_tf32) o = tf32_round4(o);
-        *reinterpret_cast<float4 *>(h1 + v * D_ + 4 * lane) = o;
-    }
+    StarCtx c;
+    c.n = n; c.i = i; c.b = b; c.hd = warp; c.g = lane >> 2; c.t = lane & 3;
+    c.m1 = TM1[warp]; c.m2 = TM2[warp]; c.a1 = TA1[warp];
+    c.Fh = Fs + warp * 16; c.ELs = ELs; c.ERs = ERs; c.ksteps = KP / 8;
+    c.pnum = pnum; c.pden = pden; c.pmax = pmax; c.arrive = arrive;
+    c.h = h; c.bias = bias; c.bn_scale = bn_scale; c.bn_shift = bn_shift; c.h1 = h1; c.h1_tf32 = h1_tf32;
+    const int MT = MP / 16;
+    int mt = 0;
+    for (; mt + 2 <= MT; mt += 2) star_tiles<2>(c, mt);
+    if (mt < MT) star_tiles<1>(c, mt);
 }
 
 }  // namespace
 
 extern "C" int gnngls_gat_aggregate_csr(const int32_t *indptr, const int32_t *indices, int64_t M, const float *ft,
                                         const float *el, const float *er, const float *h, const float *gat_bias,
-                                        const float *bn_scale, const float *bn_shift, float *h1, int round_tf32,
+                                        const float *bn_scale, const float *bn_shift, float *h1, float *h1_tf32,
                                         void *stream) {
     GNNGLS_REQUIRE(indptr && indices && ft && el && er && h && bn_scale && bn_shift && h1, GNNGLS_ERR_BAD_ARG,
                    "null pointer argument");
@@ -338,19 +385,20 @@ extern "C" int gnngls_gat_aggregate_csr(const int32_t *indptr, const int32_t *in
     const int64_t blocks = (M + CSR_WARPS - 1) / CSR_WARPS;
     const int64_t cap = (int64_t)gnngls::device_sm_count() * 64;
     gat_csr_kernel<<<(int)(blocks < cap ? blocks : cap), CSR_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        indptr, indices, M, ft, el, er, h, gat_bias, bn_scale, bn_shift, h1, round_tf32);
+        indptr, indices, M, ft, el, er, h, gat_bias, bn_scale, bn_shift, h1, h1_tf32);
     GNNGLS_LAUNCH_OK("gat_csr_kernel");
     return GNNGLS_OK;
 }
 
 extern "C" size_t gnngls_gat_kn_workspace_bytes(int B, int n) {
     if (B <= 0 || n <= 0) return 0;
-    return sizeof(float) * (size_t)B * n * n * (D_ + 2 * H_);
+    const size_t N = (size_t)n * (n - 1) / 2;
+    return sizeof(float) * (size_t)B * n * n * (D_ + 2 * H_) + sizeof(int) * (size_t)B * N * H_;
 }
 
 extern "C" int gnngls_gat_aggregate_kn(int B, int n, const float *ft, const float *el, const float *er,
                                        const float *h, const float *gat_bias, const float *bn_scale,
-                                       const float *bn_shift, float *h1, int round_tf32, void *workspace,
+                                       const float *bn_shift, float *h1, float *h1_tf32, void *workspace,
                                        size_t workspace_bytes, void *stream) {
     GNNGLS_REQUIRE(ft && el && er && h && bn_scale && bn_shift && h1, GNNGLS_ERR_BAD_ARG, "null pointer argument");
     GNNGLS_REQUIRE(n >= 3, GNNGLS_ERR_UNSUPPORTED, "line graph of K_n needs n >= 3 (got %d)", n);
@@ -362,14 +410,16 @@ extern "C" int gnngls_gat_aggregate_kn(int B, int n, const float *ft, const floa
     GNNGLS_REQUIRE(workspace && workspace_bytes >= gnngls_gat_kn_workspace_bytes(B, n), GNNGLS_ERR_WORKSPACE,
                    "gat_kn workspace too small: need %zu bytes", gnngls_gat_kn_workspace_bytes(B, n));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t N = (size_t)n * (n - 1) / 2;
     float *pnum = static_cast<float *>(workspace);
     float *pden = pnum + (size_t)B * n * n * D_;
     float *pmax = pden + (size_t)B * n * n * H_;
+    int *arrive = reinterpret_cast<int *>(pmax + (size_t)B * n * n * H_);
+    GNNGLS_CUDA_OK(cudaMemsetAsync(arrive, 0, sizeof(int) * (size_t)B * N * H_, st));
     if (smem > 48 * 1024)
         GNNGLS_CUDA_OK(cudaFuncSetAttribute(gat_kn_star_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gat_kn_star_kernel<<<B * n, STAR_THREADS, smem, st>>>(n, ft, el, er, pnum, pden, pmax);
+    gat_kn_star_kernel<<<B * n, STAR_THREADS, smem, st>>>(n, ft, el, er, pnum, pden, pmax, arrive, h, gat_bias,
+                                                          bn_scale, bn_shift, h1, h1_tf32);
     GNNGLS_LAUNCH_OK("gat_kn_star_kernel");
-    gat_kn_combine_kernel<<<B * n, 128, 0, st>>>(n, pnum, pden, pmax, h, gat_bias, bn_scale, bn_shift, h1, round_tf32);
-    GNNGLS_LAUNCH_OK("gat_kn_combine_kernel");
     return GNNGLS_OK;
 }

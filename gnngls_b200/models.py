@@ -74,12 +74,14 @@ class GATConv(nn.Module):
         M = G.number_of_nodes()
         zero = torch.zeros(M, self._in_feats, dtype=torch.float32, device=feat.device)
         one = torch.ones(self._in_feats, dtype=torch.float32, device=feat.device)
-        out = _gat_block(G, feat.contiguous(), zero, self.fc.weight.detach().contiguous(),
-                         self.attn_l.detach().reshape(-1).contiguous(), self.attn_r.detach().reshape(-1).contiguous(),
-                         None if self.bias is None else self.bias.detach().contiguous(), one,
-                         torch.zeros_like(one), _ops.DENSE_SIMT if _dense_impl_default() == 'simt' else _ops.DENSE_TCGEN05,
-                         'auto', {})
-        return out.view(M, self._num_heads, self._out_feats)
+        tc = _dense_impl_default() != 'simt'
+        feat = feat.detach().float().contiguous()
+        W = self.fc.weight.detach().float().contiguous()
+        out, _ = _gat_block(G, tf32_round(feat) if tc else feat, zero, tf32_round(W) if tc else W,
+                            self.attn_l.detach().reshape(-1).contiguous(), self.attn_r.detach().reshape(-1).contiguous(),
+                            None if self.bias is None else self.bias.detach().contiguous(), one,
+                            torch.zeros_like(one), _ops.DENSE_TCGEN05 if tc else _ops.DENSE_SIMT, 'auto', {})
+        return out.clone().view(M, self._num_heads, self._out_feats)
 
 
 def tf32_round(t):
@@ -109,19 +111,21 @@ def _buf(ws, name, shape, dtype, device):
     return t[:numel].view(*shape)
 
 
-def _gat_block(G, h, skip, Wfc, al, ar, bias, bn_scale, bn_shift, dense_impl, gat_impl, ws):
-    """fc + aggregate(+skip+BN1).  Returns h1 [M,128]."""
+def _gat_block(G, h_op, skip, Wfc, al, ar, bias, bn_scale, bn_shift, dense_impl, gat_impl, ws):
+    """fc + aggregate(+skip+BN1).  `h_op` is the fc operand (the TF32-rounded copy on the tensor-core
+    path), `skip` the unrounded activation.  Returns (h1, h1_tf32 or None), both [M,128]."""
     lib = _lib.load()
-    M, dev = h.shape[0], h.device
+    M, dev = h_op.shape[0], h_op.device
     st = _ops._stream()
+    tc = dense_impl == _ops.DENSE_TCGEN05
     ft = _buf(ws, 'ft', (M, 128), torch.float32, dev)
     el = _buf(ws, 'el', (M, 8), torch.float32, dev)
     er = _buf(ws, 'er', (M, 8), torch.float32, dev)
     h1 = _buf(ws, 'h1', (M, 128), torch.float32, dev)
+    h1r = _buf(ws, 'h1_tf32', (M, 128), torch.float32, dev) if tc else None
     p = _ops._ptr
-    rnd = 1 if dense_impl == _ops.DENSE_TCGEN05 else 0
     with stage('fc'):
-        _lib.check(lib.gnngls_fc_forward(dense_impl, p(h), M, p(Wfc), p(al), p(ar), p(ft), p(el), p(er), st))
+        _lib.check(lib.gnngls_fc_forward(dense_impl, p(h_op), M, p(Wfc), p(al), p(ar), p(ft), p(el), p(er), st))
     use_kn = gat_impl == 'kn' or (gat_impl == 'auto' and G.kind == 'kn' and G.n <= 380)
     if use_kn:
         if G.kind != 'kn':
@@ -130,13 +134,13 @@ def _gat_block(G, h, skip, Wfc, al, ar, bias, bn_scale, bn_shift, dense_impl, ga
         wk = _buf(ws, 'gat_ws', (nbytes,), torch.uint8, dev)
         with stage('gat_kn'):
             _lib.check(lib.gnngls_gat_aggregate_kn(G.batch_size, G.n, p(ft), p(el), p(er), p(skip), p(bias),
-                                                   p(bn_scale), p(bn_shift), p(h1), rnd, p(wk), nbytes, st))
+                                                   p(bn_scale), p(bn_shift), p(h1), p(h1r), p(wk), nbytes, st))
     else:
         indptr, indices = G.csr()
         with stage('gat_csr'):
             _lib.check(lib.gnngls_gat_aggregate_csr(p(indptr), p(indices), M, p(ft), p(el), p(er), p(skip), p(bias),
-                                                    p(bn_scale), p(bn_shift), p(h1), rnd, st))
-    return h1
+                                                    p(bn_scale), p(bn_shift), p(h1), p(h1r), st))
+    return h1, h1r
 
 
 class AttentionLayer(nn.Module):
@@ -165,7 +169,10 @@ class AttentionLayer(nn.Module):
             d[k + '_tf32'] = tf32_round(d[k])
         return d
 
-    def forward(self, G, x, _params=None, _ws=None, _dense_impl=None, _gat_impl='auto', _out=None):
+    def forward(self, G, x, _params=None, _ws=None, _dense_impl=None, _gat_impl='auto', _out=None, _x_tf32=None,
+                _out_tf32=None):
+        """Public form: forward(G, x) -> [M,128].  The underscore arguments let the model reuse buffers and
+        pass the TF32-rounded operand copies between layers."""
         if self.training:
             raise NotImplementedError('gnngls_b200 implements the inference path only: call model.eval()')
         if self._dims != (128, 8, 512):
@@ -175,18 +182,22 @@ class AttentionLayer(nn.Module):
         ws = _ws if _ws is not None else {}
         impl = _dense_impl if _dense_impl is not None else (
             _ops.DENSE_SIMT if _dense_impl_default() == 'simt' else _ops.DENSE_TCGEN05)
+        tc = impl == _ops.DENSE_TCGEN05
         x = x.contiguous()
         M, dev = x.shape[0], x.device
-        sfx = '_tf32' if impl == _ops.DENSE_TCGEN05 else ''
-        h1 = _gat_block(G, x, x, prm['Wfc' + sfx], prm['al'], prm['ar'], prm['gbias'], prm['s1'], prm['t1'], impl, _gat_impl, ws)
+        sfx = '_tf32' if tc else ''
+        if tc and _x_tf32 is None:
+            _x_tf32 = tf32_round(x)
+        h1, h1r = _gat_block(G, _x_tf32 if tc else x, x, prm['Wfc' + sfx], prm['al'], prm['ar'], prm['gbias'],
+                             prm['s1'], prm['t1'], impl, _gat_impl, ws)
         nbytes = lib.gnngls_ff_workspace_bytes(impl, M)
         wk = _buf(ws, 'ff_ws', (nbytes,), torch.uint8, dev)
         out = _out if _out is not None else torch.empty(M, 128, dtype=torch.float32, device=dev)
         p = _ops._ptr
         with stage('ff'):
-            _lib.check(lib.gnngls_ff_forward(impl, p(h1), M, p(prm['W1' + sfx]), p(prm['b1']), p(prm['W2' + sfx]),
-                                             p(prm['b2']), p(prm['s2']), p(prm['t2']), p(out), p(wk), nbytes,
-                                             _ops._stream()))
+            _lib.check(lib.gnngls_ff_forward(impl, p(h1), p(h1r), M, p(prm['W1' + sfx]), p(prm['b1']),
+                                             p(prm['W2' + sfx]), p(prm['b2']), p(prm['s2']), p(prm['t2']), p(out),
+                                             p(_out_tf32), p(wk), nbytes, _ops._stream()))
         return out
 
 
@@ -240,15 +251,19 @@ class EdgePropertyPredictionModel(nn.Module):
         in_dim, out_dim = self.embed_layer.in_features, self.decision_layer.out_features
         p = _ops._ptr
         with torch.cuda.device(dev):
+            tc = impl == _ops.DENSE_TCGEN05
             ha = _buf(self._ws, 'ha', (M, 128), torch.float32, dev)
             hb = _buf(self._ws, 'hb', (M, 128), torch.float32, dev)
+            har = _buf(self._ws, 'ha_tf32', (M, 128), torch.float32, dev) if tc else None
+            hbr = _buf(self._ws, 'hb_tf32', (M, 128), torch.float32, dev) if tc else None
             with stage('embed'):
-                _lib.check(lib.gnngls_embed_forward(p(x), M, in_dim, p(prm['We']), p(prm['be']), p(ha),
-                                                    1 if impl == _ops.DENSE_TCGEN05 else 0, _ops._stream()))
-            cur, nxt = ha, hb
+                _lib.check(lib.gnngls_embed_forward(p(x), M, in_dim, p(prm['We']), p(prm['be']), p(ha), p(har),
+                                                    _ops._stream()))
+            cur, nxt, cur_r, nxt_r = ha, hb, har, hbr
             for layer, lp in zip(self.message_passing_layers, prm['layers']):
-                layer(G, cur, _params=lp, _ws=self._ws, _dense_impl=impl, _gat_impl=self.gat_impl, _out=nxt)
-                cur, nxt = nxt, cur
+                layer(G, cur, _params=lp, _ws=self._ws, _dense_impl=impl, _gat_impl=self.gat_impl, _out=nxt,
+                      _x_tf32=cur_r, _out_tf32=nxt_r)
+                cur, nxt, cur_r, nxt_r = nxt, cur, nxt_r, cur_r
             y = torch.empty(M, out_dim, dtype=torch.float32, device=dev)
             with stage('decision'):
                 _lib.check(lib.gnngls_decision_forward(p(cur), M, out_dim, p(prm['Wd']), p(prm['bd']), p(y),

@@ -20,6 +20,14 @@ class Scalers:
     regret_scale: float = 1.0                           # synthetic default: data_min=0, data_max=1
     regret_min: float = 0.0
 
+    def calibrated(self, y, clamp_frac=0.05, span=0.3):
+        """Synthetic regret scaler for UNTRAINED (random-init) weights, whose raw outputs are an arbitrary
+        near-constant: map the [clamp_frac, 1-clamp_frac] quantile range of `y` onto [0, span] so that, as with a
+        trained model, a few percent of the predicted regrets clamp to exactly 0 and the rest are spread out."""
+        q = torch.quantile(y.detach().float().flatten()[:1 << 22], torch.tensor([clamp_frac, 1 - clamp_frac], device=y.device))
+        lo, hi = float(q[0]), float(q[1])
+        return Scalers(self.feat_scale, self.feat_min, max(hi - lo, 1e-6) / span, lo)
+
     @classmethod
     def from_sklearn(cls, scalers):
         f, r = scalers['features'], scalers['regret']
@@ -51,6 +59,16 @@ class RegretGLS:
         if key not in self._graphs:
             self._graphs[key] = LineGraph.complete(n, b, device)
         return self._graphs[key]
+
+    @torch.no_grad()
+    def calibrate_synthetic_regret_scaler(self, D):
+        """See Scalers.calibrated(); uses the raw model outputs of (at most) one micro-batch of D."""
+        n = D.shape[-1]
+        b = min(D.shape[0], self.micro_batch)
+        x = _ops.edge_features(D[:b].contiguous(), self.scalers.feat_scale, self.scalers.feat_min)
+        y = self.model(self._graph(n, b, D.device), x.reshape(-1, 1))
+        self.scalers = self.scalers.calibrated(y)
+        return self.scalers
 
     @torch.no_grad()
     def predict_regret(self, D):

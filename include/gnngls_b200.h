@@ -145,7 +145,7 @@ int gnngls_edge_features(const double *D, int B, int n, double scale, double min
 
 /* embed_layer (models.py:57,66): h[M,128] = x[M,in_dim] * W[128,in_dim]^T + b */
 int gnngls_embed_forward(const float *x, int64_t M, int in_dim, const float *W, const float *b,
-                         float *h, int round_tf32, void *stream);
+                         float *h, float *h_tf32 /* or NULL */, void *stream);
 
 /* dense implementation selector for the fc / feed-forward contractions */
 typedef enum gnngls_dense_impl {
@@ -161,16 +161,18 @@ int gnngls_fc_forward(int impl, const float *h, int64_t M, const float *Wfc, con
 /* Per-channel affine form of eval-mode BatchNorm1d: y = x*scale + shift
  * (scale = gamma/sqrt(var+eps), shift = beta - mean*scale; models.py:27,35).
  *
- * round_tf32 (embed / aggregate): store the produced activations rounded to TF32 (cvt.rna), so
- * that the tcgen05 kind::tf32 consumer — which ignores the low 13 mantissa bits of its operands —
- * sees round-to-nearest instead of truncated inputs.  Pass 0 for the pure-fp32 debug path. */
+ * *_tf32 outputs (embed / aggregate / feed-forward, all nullable): a second copy of the produced
+ * activation rounded to TF32 (cvt.rna).  The tcgen05 kind::tf32 MMA ignores the low 13 mantissa
+ * bits of its operands (truncation, a biased error ~10x larger than rounding over this 8-layer
+ * model); feeding it the pre-rounded copy makes that truncation exact, while skip connections keep
+ * reading the unrounded fp32 activation.  Pass NULL on the pure-fp32 debug path. */
 
 /* GAT aggregate over an arbitrary destination-sorted CSR graph + skip + BatchNorm1 (models.py:12-15,27):
  *   h1[v] = BN1(h[v] + sum_u softmax_u(leaky_relu(el[u]+er[v])) ft[u] + gat_bias)               */
 int gnngls_gat_aggregate_csr(const int32_t *indptr, const int32_t *indices, int64_t M,
                              const float *ft, const float *el, const float *er, const float *h,
                              const float *gat_bias /* [128] or NULL */, const float *bn_scale,
-                             const float *bn_shift, float *h1, int round_tf32, void *stream);
+                             const float *bn_shift, float *h1, float *h1_tf32, void *stream);
 
 /* Same op for a batch of line graphs of K_n with the adjacency computed arithmetically
  * (neighbours of (i,j) are (i,k) and (k,j)); M = B*n(n-1)/2.  `workspace` must hold
@@ -178,16 +180,18 @@ int gnngls_gat_aggregate_csr(const int32_t *indptr, const int32_t *indices, int6
 size_t gnngls_gat_kn_workspace_bytes(int B, int n);
 int gnngls_gat_aggregate_kn(int B, int n, const float *ft, const float *el, const float *er,
                             const float *h, const float *gat_bias, const float *bn_scale,
-                            const float *bn_shift, float *h1, int round_tf32, void *workspace,
+                            const float *bn_shift, float *h1, float *h1_tf32, void *workspace,
                             size_t workspace_bytes, void *stream);
 
 /* feed-forward block (models.py:28-35):
  *   h_out = BN2(h1 + W2 * relu(W1 * h1 + b1) + b2),  W1[512,128], W2[128,512]
+ * h1_tf32 (nullable) is the operand of the first contraction; the skip always reads h1.
  * `workspace` must hold gnngls_ff_workspace_bytes(impl, M) bytes (may be 0). */
 size_t gnngls_ff_workspace_bytes(int impl, int64_t M);
-int gnngls_ff_forward(int impl, const float *h1, int64_t M, const float *W1, const float *b1,
-                      const float *W2, const float *b2, const float *bn_scale, const float *bn_shift,
-                      float *h_out, void *workspace, size_t workspace_bytes, void *stream);
+int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32, int64_t M, const float *W1,
+                      const float *b1, const float *W2, const float *b2, const float *bn_scale,
+                      const float *bn_shift, float *h_out, float *h_out_tf32, void *workspace,
+                      size_t workspace_bytes, void *stream);
 
 /* decision_layer (models.py:63,69): y[M,out_dim] = h * Wd[out_dim,128]^T + bd */
 int gnngls_decision_forward(const float *h, int64_t M, int out_dim, const float *Wd, const float *bd,

@@ -111,6 +111,8 @@ class GATConvPort(nn.Module):
         ft = self.fc(feat).view(N, H, F)
         el = (ft * self.attn_l).sum(-1)
         er = (ft * self.attn_r).sum(-1)
+        if getattr(self, '_tf32_aggregate', False):
+            ft = tf32_round(ft)
         deg = getattr(graph, 'regular_degree', None)
         if deg is not None:
             # same formula on a dst-sorted constant-degree graph, without scatter ops (faster on CPU)
@@ -199,3 +201,40 @@ def randomize_bn_stats(model, seed=1):
                 m.weight.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
                 m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
     return model
+
+
+# ---------------------------------------------------------------------------------------------
+# TF32 emulation: what an "allow_tf32" evaluation of the same model computes.  torch 1.11 (the
+# reference's pin) enables TF32 matmuls by default on Ampere+, i.e. GEMM operands are rounded to a
+# 10-bit mantissa and products are accumulated in fp32.  Used to calibrate the GPU tolerance.
+# ---------------------------------------------------------------------------------------------
+def tf32_round(t):
+    """Round to TF32 (nearest, ties away from zero == PTX cvt.rna.tf32.f32); keeps dtype."""
+    f = t.detach().to(torch.float32).contiguous()
+    r = ((f.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return r.to(t.dtype)
+
+
+class emulate_tf32:
+    """Context manager: every nn.Linear with in_features >= 128 rounds its input and weight to TF32
+    (exact products, wide accumulation when the model is .double()); GATConvPort additionally rounds
+    the aggregated features, like the tensor-core aggregate kernel."""
+
+    def __init__(self, model, round_aggregate=True):
+        self.model, self.round_aggregate, self._saved = model, round_aggregate, []
+
+    def __enter__(self):
+        for m in self.model.modules():
+            if isinstance(m, nn.Linear) and m.in_features >= 128 and m.out_features >= 128:
+                self._saved.append((m, m.forward))
+                m.forward = (lambda x, m=m: torch.nn.functional.linear(tf32_round(x), tf32_round(m.weight), m.bias))
+            if isinstance(m, GATConvPort):
+                m._tf32_aggregate = self.round_aggregate
+        return self
+
+    def __exit__(self, *exc):
+        for m, f in self._saved:
+            m.forward = f
+        for m in self.model.modules():
+            if isinstance(m, GATConvPort):
+                m._tf32_aggregate = False

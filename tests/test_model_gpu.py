@@ -1,10 +1,14 @@
 """GPU parity of EdgePropertyPredictionModel (through the C ABI) against the reference's own
 models.py outputs (golden, fp64 yardstick) and the torch oracle.
 
-Tolerances (scaled regret output, |y| = O(1)):
-  fp32 path  (SIMT dense + CSR aggregate):  max|y - y64| <= 2e-4   (fp32 torch oracle itself: <5e-5)
-  TF32 paths (tcgen05 dense and/or mma.sync K_n aggregate): max|y - y64| <= 2e-2 and
-             <= 3e-3 against an oracle whose GEMM operands are rounded to TF32 the same way.
+Tolerances on the raw model output (|y| ~ 30 for the seeded random-init weights), yardstick = the
+reference's own models.py evaluated in fp64 (golden `y64`):
+  fp32 path  (SIMT dense + CSR aggregate): max|y - y64| <= 1e-5 * max|y64|
+             (the fp32 torch oracle itself is within 2e-6 * max|y64| of fp64);
+  TF32 paths (tcgen05 dense and/or mma.sync K_n aggregate): max|y - y64| <= 2 * E_tf32 + 1e-4 * max|y64|,
+             where E_tf32 is the error of the SAME oracle evaluated with TF32-rounded GEMM operands
+             (what torch 1.11's default allow_tf32 computes on Ampere+; oracle.model_port.emulate_tf32),
+             measured per case at test time (E_tf32 ~ 1.2e-2 .. 2.2e-2 here, i.e. ~5e-4 relative).
 """
 import numpy as np
 import pytest
@@ -17,7 +21,17 @@ from tests import _golden
 pytestmark = pytest.mark.gpu
 
 MODEL, TOP = _golden.load('model')
-TOL_FP32, TOL_TF32 = 2e-4, 2e-2
+REL_FP32 = 1e-5
+
+
+def tf32_budget(port, n, B, x, y64):
+    """2 x (error of the TF32-emulating oracle vs fp64) + 1e-4 * max|y64|."""
+    g = model_port.EdgeListGraph.kn_line_graph(n, batch=B)
+    port = port.double()
+    with torch.no_grad(), model_port.emulate_tf32(port):
+        yt = port(g, torch.as_tensor(x).double()).numpy()
+    port.float()
+    return 2 * np.abs(yt - y64).max() + 1e-4 * np.abs(y64).max()
 
 
 def make_models(gat_bias=False):
@@ -40,15 +54,15 @@ def run(m, n, B, x, dense, gat):
         return m(G, torch.as_tensor(x).cuda()).cpu().numpy()
 
 
-@pytest.mark.parametrize('dense,gat,tol', [('simt', 'csr', TOL_FP32), ('simt', 'kn', TOL_TF32),
-                                           ('tcgen05', 'csr', TOL_TF32), ('tcgen05', 'kn', TOL_TF32)])
-def test_model_matches_reference_golden(dense, gat, tol):
-    _, m = make_models()
+@pytest.mark.parametrize('dense,gat', [('simt', 'csr'), ('simt', 'kn'), ('tcgen05', 'csr'), ('tcgen05', 'kn')])
+def test_model_matches_reference_golden(dense, gat):
+    port, m = make_models()
     for c in MODEL:
         n, B = c.nB.tolist()
         y = run(m, n, B, c.x, dense, gat)
         err = np.abs(y - c.y64).max()
-        print(f'{dense}+{gat} n={n} B={B}: max|y-y64|={err:.3e} (|y|max={np.abs(c.y64).max():.3f})')
+        tol = REL_FP32 * np.abs(c.y64).max() if (dense, gat) == ('simt', 'csr') else tf32_budget(port, n, B, c.x, c.y64)
+        print(f'{dense}+{gat} n={n} B={B}: max|y-y64|={err:.3e} tol={tol:.3e} (|y|max={np.abs(c.y64).max():.3f})')
         assert y.shape == c.y64.shape and np.isfinite(y).all()
         assert err <= tol, (dense, gat, n, err)
 
@@ -63,8 +77,16 @@ def test_paths_agree_and_batching_is_transparent():
     for b in range(B):          # batched == per-instance (eval-mode BN is per-node)
         yb = run(m, n, 1, x[b * N:(b + 1) * N], 'simt', 'csr')
         assert np.array_equal(yb, ref[b * N:(b + 1) * N])
-    assert np.abs(run(m, n, B, x, 'simt', 'kn') - ref).max() < TOL_TF32
-    assert np.abs(run(m, n, B, x, 'tcgen05', 'kn') - ref).max() < TOL_TF32
+    with torch.no_grad():
+        y64 = port.double()(model_port.EdgeListGraph.kn_line_graph(n, B), torch.as_tensor(x).double()).numpy()
+    port.float()
+    assert np.abs(ref - y64).max() < REL_FP32 * np.abs(y64).max()
+    tol = tf32_budget(port, n, B, x, y64)
+    assert np.abs(run(m, n, B, x, 'simt', 'kn') - y64).max() < tol
+    assert np.abs(run(m, n, B, x, 'tcgen05', 'kn') - y64).max() < tol
+    yk = run(m, n, B, x, 'tcgen05', 'kn')
+    for b in range(B):          # TF32 path: batching is transparent too (bitwise)
+        assert np.array_equal(run(m, n, 1, x[b * N:(b + 1) * N], 'tcgen05', 'kn'), yk[b * N:(b + 1) * N])
     # arbitrary-CSR entry point (edge list in random order) == K_n graph
     s, d = model_port.kn_line_graph_edges(n)
     perm = np.random.default_rng(0).permutation(len(s))
@@ -72,10 +94,7 @@ def test_paths_agree_and_batching_is_transparent():
     m.dense_impl, m.gat_impl = 'simt', 'auto'
     with torch.no_grad():
         y1 = m(g, torch.as_tensor(x[:N]).cuda()).cpu().numpy()
-    assert np.abs(y1 - ref[:N]).max() < 1e-5
-    with torch.no_grad():
-        y64 = port.double()(model_port.EdgeListGraph.kn_line_graph(n, B), torch.as_tensor(x).double()).numpy()
-    assert np.abs(ref - y64).max() < TOL_FP32
+    assert np.abs(y1 - ref[:N]).max() < REL_FP32 * np.abs(y64).max()
 
 
 def test_gat_bias_checkpoints():
@@ -85,8 +104,9 @@ def test_gat_bias_checkpoints():
     x = (instances.edge_features(D) / np.float32(np.sqrt(2))).reshape(-1, 1)
     with torch.no_grad():
         y64 = port.double()(model_port.EdgeListGraph.kn_line_graph(n, B), torch.as_tensor(x).double()).numpy()
-    assert np.abs(run(m, n, B, x, 'simt', 'csr') - y64).max() < TOL_FP32
-    assert np.abs(run(m, n, B, x, 'tcgen05', 'kn') - y64).max() < TOL_TF32
+    port.float()
+    assert np.abs(run(m, n, B, x, 'simt', 'csr') - y64).max() < REL_FP32 * np.abs(y64).max()
+    assert np.abs(run(m, n, B, x, 'tcgen05', 'kn') - y64).max() < tf32_budget(port, n, B, x, y64)
 
 
 def _tf32(t):
@@ -112,26 +132,29 @@ def test_dense_kernels_against_tf32_rounded_oracle():
             hh = models.tf32_round(h) if tc else h
             Wd = models.tf32_round(W) if tc else W
             W1d, W2d = (models.tf32_round(W1), models.tf32_round(W2)) if tc else (W1, W2)
-            hd = hh.cuda()
+            hd, Wc, alc, arc = hh.cuda(), Wd.cuda(), al.cuda(), ar.cuda()      # keep device copies alive
+            W1c, b1c, W2c, b2c, scc, shc = W1d.cuda(), b1.cuda(), W2d.cuda(), b2.cuda(), sc.cuda(), sh.cuda()
             ft = torch.empty(M, 128, device='cuda'); el = torch.empty(M, 8, device='cuda'); er = torch.empty(M, 8, device='cuda')
-            _lib.check(lib.gnngls_fc_forward(impl, p(hd), M, p(Wd.cuda()), p(al.cuda()), p(ar.cuda()), p(ft), p(el), p(er),
+            _lib.check(lib.gnngls_fc_forward(impl, p(hd), M, p(Wc), p(alc), p(arc), p(ft), p(el), p(er),
                                              _ops._stream()))
             ft64 = hh.double() @ Wd.double().t()
             el64 = (ft64.view(M, 8, 16) * al.double().view(1, 8, 16)).sum(-1)
             er64 = (ft64.view(M, 8, 16) * ar.double().view(1, 8, 16)).sum(-1)
-            tol = 2e-3 if tc else 1e-4         # tc: ft is stored TF32-rounded (|ft| ~ 1 -> 5e-4)
-            assert (ft.cpu().double() - ft64).abs().max() < tol, (M, impl)
+            assert (ft.cpu().double() - ft64).abs().max() < 1e-4, (M, impl)
             assert (el.cpu().double() - el64).abs().max() < 1e-4 and (er.cpu().double() - er64).abs().max() < 1e-4
             nbytes = lib.gnngls_ff_workspace_bytes(impl, M)
             ws = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
             out = torch.empty(M, 128, device='cuda')
-            _lib.check(lib.gnngls_ff_forward(impl, p(hd), M, p(W1d.cuda()), p(b1.cuda()), p(W2d.cuda()), p(b2.cuda()),
-                                             p(sc.cuda()), p(sh.cuda()), p(out), p(ws), nbytes, _ops._stream()))
+            out_r = torch.empty(M, 128, device='cuda')
+            _lib.check(lib.gnngls_ff_forward(impl, p(hd), p(hd), M, p(W1c), p(b1c), p(W2c), p(b2c), p(scc), p(shc), p(out),
+                                             p(out_r), p(ws), nbytes, _ops._stream()))
+            torch.cuda.synchronize()
             hid = torch.relu(hh.double() @ W1d.double().t() + b1.double())
             if tc:
                 hid = _tf32(hid)
             o64 = (hh.double() + hid @ W2d.double().t() + b2.double()) * sc.double() + sh.double()
-            assert (out.cpu().double() - o64).abs().max() < (3e-3 if tc else 2e-4), (M, impl)
+            assert (out.cpu().double() - o64).abs().max() < (1e-3 if tc else 2e-4), (M, impl)
+            assert torch.equal(out_r.cpu(), models.tf32_round(out.cpu()))
 
 
 def test_glue_kernels_bit_exact():
@@ -158,9 +181,10 @@ def test_pipeline_tours_bit_exact_given_gpu_regrets():
     n, B, K = 20, 24, 5
     _, D = instances.random_instances(B, n, seed=6)
     solver = pipeline.RegretGLS(m, micro_batch=7)
+    solver.calibrate_synthetic_regret_scaler(torch.as_tensor(D).cuda())
     res = solver.solve(torch.as_tensor(D).cuda(), n_iters=K, perturbation_moves=20, keep_regret=True)
     regret = res.regret.cpu().numpy()
-    assert regret.min() >= 0 and (regret > 0).any()
+    assert regret.min() >= 0 and 0.01 < (regret == 0).mean() < 0.2 and regret.max() < 1.0
     o_t, o_c = gls_port.pipeline_batch(D, regret, K, 20, nthreads=4)
     assert np.array_equal(res.best_tours.cpu().numpy(), o_t)
     assert np.array_equal(_golden.bits(res.best_costs.cpu().numpy()), _golden.bits(o_c))
