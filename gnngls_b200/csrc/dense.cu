@@ -168,6 +168,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -381,14 +382,14 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// row-major fp32 [rows, cols] -> box [128 rows, 32 cols], 128B swizzle, zero fill out of bounds
-int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols) {
+// row-major fp32 [rows, cols] -> box [box_rows rows, 32 cols], 128B swizzle, zero fill out of bounds
+int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint32_t box_rows = BM) {
     EncodeTiledFn fn = get_encode_fn();
     GNNGLS_REQUIRE(fn, GNNGLS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     GNNGLS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, GNNGLS_ERR_BAD_ARG, "TMA operand not 16-byte aligned");
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstr[1] = {cols * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -409,6 +410,219 @@ int launch_tc_gemm(const float *A, const float *W, const EpiParams &p, cudaStrea
     const int grid = (int)(work < sms ? work : sms);
     kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
     GNNGLS_LAUNCH_OK("gemm_tf32_kernel");
+    return GNNGLS_OK;
+}
+
+// ================================================================================================
+// Fused feed-forward block on tcgen05:  h_out = BN2(h1 + relu(h1 W1^T + b1) W2^T + b2)
+//
+// One persistent CTA per 128-row tile; the 128x512 hidden activation never leaves the SM:
+//   * the A tile (TF32 copy of h1, 64 KB) stays resident in shared memory for the whole tile;
+//   * W1 / W2 stream through a 6-stage TMA ring in chunks of 32 hidden units (16 KB per stage);
+//   * GEMM1(c): D1[c&1] (TMEM, 32 cols) = A . W1c^T            (16 x tcgen05.mma 128x32x8)
+//   * epilogue-1 (4 warps per chunk parity): tcgen05.ld -> +b1, ReLU, cvt.rna.tf32 -> written to
+//     shared memory in the 128B-swizzled K-major layout the tensor core expects (hidden chunk as
+//     the A operand of the second contraction), fence.proxy.async, mbarrier to the MMA thread;
+//   * GEMM2(c): D2 (TMEM, 128 cols) += Hc . W2c^T               (4 x tcgen05.mma 128x128x8)
+//   * final epilogue (8 warps): tcgen05.ld D2 -> +b2 + skip(h1 fp32) -> BN2 -> h_out (+ TF32 copy).
+// The MMA thread issues GEMM1(c+1) before GEMM2(c) so the tensor core works while epilogue-1 runs.
+// ================================================================================================
+constexpr int FF_HC = 32;                              // hidden units per chunk
+constexpr int FF_CHUNKS = HID_ / FF_HC;                // 16
+constexpr int FF_WSTAGES = 6;
+constexpr int FF_WSTAGE_BYTES = 16384;                 // W1c: 4 boxes [32 x 32]; W2c: 1 box [128 x 32]
+constexpr int FF_A_BYTES = BM * D_ * 4;                // 64 KB: 4 boxes [128 x 32]
+constexpr int FF_H_BYTES = BM * FF_HC * 4;             // 16 KB per buffer
+constexpr int FF_SVEC = 3 * D_ + HID_;                 // b2 | bn_scale | bn_shift | b1
+constexpr int FF_THREADS = 11 * 32;                    // warp0 W-TMA, warp1 MMA, warps 2..9 epilogue, warp10 A-TMA
+constexpr int FF_NBARS = 2 + 2 * FF_WSTAGES + 8 + 2;
+constexpr size_t FF_SMEM = 1024 + FF_A_BYTES + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES + 2 * FF_H_BYTES + FF_SVEC * 4 +
+                           FF_NBARS * 8 + 16;
+
+__global__ void __launch_bounds__(FF_THREADS, 1)
+ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
+                     const __grid_constant__ CUtensorMap tmW2, const EpiParams p, const float *__restrict__ b1) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char *sA = smem;
+    unsigned char *sW = sA + FF_A_BYTES;
+    unsigned char *sH = sW + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES;
+    float *svec = reinterpret_cast<float *>(sH + 2 * FF_H_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(svec + FF_SVEC);
+    uint64_t *a_full = bars, *a_empty = bars + 1, *w_full = bars + 2, *w_empty = w_full + FF_WSTAGES;
+    uint64_t *d1_full = w_empty + FF_WSTAGES, *d1_empty = d1_full + 2, *h_full = d1_empty + 2, *h_empty = h_full + 2;
+    uint64_t *d2_full = h_empty + 2, *d2_empty = d2_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m_tiles = (p.M + BM - 1) / BM;
+
+    for (int c = threadIdx.x; c < D_; c += FF_THREADS) { svec[c] = p.v0[c]; svec[D_ + c] = p.v1[c]; svec[2 * D_ + c] = p.v2[c]; }
+    for (int c = threadIdx.x; c < HID_; c += FF_THREADS) svec[3 * D_ + c] = b1[c];
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        for (int s = 0; s < FF_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&d1_full[g], 1); mbar_init(&d1_empty[g], 4);
+            mbar_init(&h_full[g], 4); mbar_init(&h_empty[g], 1);
+        }
+        mbar_init(d2_full, 1); mbar_init(d2_empty, EPI_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tm_d2 = tmem_base, tm_d1 = tmem_base + BN;      // D2: cols [0,128); D1[g]: [128+32g, +32)
+
+    if (warp == 10) {
+        // ------------------------------------------------------------------ A-tile producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
+                mbar_wait(a_empty, (it & 1) ^ 1);
+                mbar_expect_tx(a_full, FF_A_BYTES);
+                for (int kb = 0; kb < D_ / BK; ++kb) tma_load_2d(&tmA, a_full, sA + kb * (BM * BK * 4), kb * BK, (int)w * BM);
+            }
+        }
+    } else if (warp == 0) {
+        // ------------------------------------------------------------------ weight producer (ring order == MMA order)
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            auto load_w1 = [&](int c) {
+                mbar_wait(&w_empty[stage], phase ^ 1);
+                unsigned char *dst = sW + (size_t)stage * FF_WSTAGE_BYTES;
+                mbar_expect_tx(&w_full[stage], FF_WSTAGE_BYTES);
+                for (int kb = 0; kb < D_ / BK; ++kb) tma_load_2d(&tmW1, &w_full[stage], dst + kb * (FF_HC * BK * 4), kb * BK, c * FF_HC);
+                if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+            };
+            auto load_w2 = [&](int c) {
+                mbar_wait(&w_empty[stage], phase ^ 1);
+                mbar_expect_tx(&w_full[stage], FF_WSTAGE_BYTES);
+                tma_load_2d(&tmW2, &w_full[stage], sW + (size_t)stage * FF_WSTAGE_BYTES, c * FF_HC, 0);
+                if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+            };
+            for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x) {
+                for (int c = 0; c < FF_CHUNKS; ++c) {
+                    load_w1(c);
+                    if (c >= 1) load_w2(c - 1);
+                }
+                load_w2(FF_CHUNKS - 1);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = make_idesc_tf32(BM, FF_HC), idesc2 = make_idesc_tf32(BM, BN);
+            uint32_t stage = 0, phase = 0, it = 0;
+            uint32_t n_d1[2] = {0, 0}, n_h[2] = {0, 0};
+            const uint32_t aA = smem_u32(sA);
+            auto gemm2 = [&](int c) {
+                const int g = c & 1;
+                mbar_wait(&h_full[g], n_h[g] & 1); ++n_h[g];          // epilogue-1 has written Hc[g]
+                mbar_wait(&w_full[stage], phase);
+                tc_fence_after();
+                const uint64_t da = make_sw128_kmajor_desc(smem_u32(sH + g * FF_H_BYTES));
+                const uint64_t db = make_sw128_kmajor_desc(smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES));
+#pragma unroll
+                for (int k = 0; k < FF_HC / 8; ++k) umma_tf32(tm_d2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (c | k) != 0);
+                umma_commit(&w_empty[stage]);
+                umma_commit(&h_empty[g]);
+                if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+            };
+            for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
+                mbar_wait(a_full, it & 1);
+                for (int c = 0; c < FF_CHUNKS; ++c) {
+                    const int g = c & 1;
+                    mbar_wait(&d1_empty[g], (n_d1[g] & 1) ^ 1); ++n_d1[g];   // epilogue-1 drained D1[g]
+                    mbar_wait(&w_full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sw = smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES);
+#pragma unroll
+                    for (int kb = 0; kb < D_ / BK; ++kb) {
+                        const uint64_t da = make_sw128_kmajor_desc(aA + kb * (BM * BK * 4));
+                        const uint64_t db = make_sw128_kmajor_desc(sw + kb * (FF_HC * BK * 4));
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k)
+                            umma_tf32(tm_d1 + g * FF_HC, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb | k) != 0);
+                    }
+                    umma_commit(&w_empty[stage]);
+                    umma_commit(&d1_full[g]);
+                    if (c == FF_CHUNKS - 1) umma_commit(a_empty);     // last reader of the A tile
+                    if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                    if (c == 1) { mbar_wait(d2_empty, (it & 1) ^ 1); tc_fence_after(); }   // before GEMM2(0) overwrites D2
+                    if (c >= 1) gemm2(c - 1);
+                }
+                gemm2(FF_CHUNKS - 1);
+                umma_commit(d2_full);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue warps
+        const int q = warp & 3;                               // TMEM lane quarter
+        const int g = (warp - 2) >> 2;                        // chunk parity handled by this warp group
+        const int r_in_tile = q * 32 + lane;
+        uint32_t n_e1 = 0, it = 0;
+        unsigned char *hrow = sH + g * FF_H_BYTES + r_in_tile * 128;
+        for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
+            for (int c = g; c < FF_CHUNKS; c += 2, ++n_e1) {
+                mbar_wait(&d1_full[g], n_e1 & 1);
+                tc_fence_after();
+                float v[32];
+                tmem_ld_32x32(tm_d1 + ((uint32_t)(q * 32) << 16) + g * FF_HC, v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d1_empty[g]);     // D1[g] is in registers now
+                mbar_wait(&h_empty[g], (n_e1 & 1) ^ 1);       // GEMM2 of chunk c-2 has finished reading Hc[g]
+                const float *bb = svec + 3 * D_ + c * FF_HC;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {                 // 16-byte piece j of this row, 128B swizzle
+                    const float4 b = *reinterpret_cast<const float4 *>(bb + 4 * j);
+                    float4 r;
+                    r.x = tf32_rna(fmaxf(v[4 * j] + b.x, 0.f)); r.y = tf32_rna(fmaxf(v[4 * j + 1] + b.y, 0.f));
+                    r.z = tf32_rna(fmaxf(v[4 * j + 2] + b.z, 0.f)); r.w = tf32_rna(fmaxf(v[4 * j + 3] + b.w, 0.f));
+                    *reinterpret_cast<float4 *>(hrow + ((j ^ (r_in_tile & 7)) << 4)) = r;
+                }
+                fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&h_full[g]);
+            }
+            // final epilogue: this group owns 64 of the 128 output columns
+            const int64_t row = w * BM + r_in_tile;
+            mbar_wait(d2_full, it & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c2 = 0; c2 < 2; ++c2) {
+                const int col = g * 64 + c2 * 32;
+                float v[32];
+                tmem_ld_32x32(tm_d2 + ((uint32_t)(q * 32) << 16) + col, v);
+                if (row < p.M) epilogue_row32<EPI_FF2>(p, svec, row, col, v);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d2_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+int launch_ff_fused(const float *a_op, const float *W1, const float *b1, const float *W2, const EpiParams &p, cudaStream_t st) {
+    CUtensorMap tmA, tmW1, tmW2;
+    if (int rc = make_map(&tmA, a_op, (uint64_t)p.M, D_, BM)) return rc;
+    if (int rc = make_map(&tmW1, W1, HID_, D_, FF_HC)) return rc;
+    if (int rc = make_map(&tmW2, W2, D_, HID_, BM)) return rc;
+    GNNGLS_CUDA_OK(cudaFuncSetAttribute(ff_fused_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
+    const int64_t tiles = (p.M + BM - 1) / BM;
+    const int sms = gnngls::device_sm_count();
+    ff_fused_tf32_kernel<<<(int)(tiles < sms ? tiles : sms), FF_THREADS, FF_SMEM, st>>>(tmA, tmW1, tmW2, p, b1);
+    GNNGLS_LAUNCH_OK("ff_fused_tf32_kernel");
     return GNNGLS_OK;
 }
 
@@ -541,8 +755,8 @@ extern "C" int gnngls_fc_forward(int impl, const float *h, int64_t M, const floa
 }
 
 extern "C" size_t gnngls_ff_workspace_bytes(int impl, int64_t M) {
-    (void)impl;
-    return M > 0 ? (size_t)M * HID_ * sizeof(float) : 0;     // hidden activations [M,512]
+    if (impl == GNNGLS_DENSE_TCGEN05) return 0;               // fused: the hidden activations stay on chip
+    return M > 0 ? (size_t)M * HID_ * sizeof(float) : 0;     // debug path materialises hidden [M,512]
 }
 
 extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32, int64_t M, const float *W1,
@@ -551,8 +765,9 @@ extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32
                                  size_t workspace_bytes, void *stream) {
     GNNGLS_REQUIRE(h1 && W1 && b1 && W2 && b2 && bn_scale && bn_shift && h_out, GNNGLS_ERR_BAD_ARG, "null pointer argument");
     if (M <= 0) return GNNGLS_OK;
-    GNNGLS_REQUIRE(workspace && workspace_bytes >= gnngls_ff_workspace_bytes(impl, M), GNNGLS_ERR_WORKSPACE,
-                   "ff workspace too small: need %zu bytes", gnngls_ff_workspace_bytes(impl, M));
+    const size_t need = gnngls_ff_workspace_bytes(impl, M);
+    GNNGLS_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), GNNGLS_ERR_WORKSPACE,
+                   "ff workspace too small: need %zu bytes", need);
     float *hid = static_cast<float *>(workspace);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     EpiParams p1{};
@@ -560,11 +775,7 @@ extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32
     EpiParams p2{};
     p2.M = M; p2.out = h_out; p2.out_tf32 = h_out_tf32; p2.v0 = b2; p2.v1 = bn_scale; p2.v2 = bn_shift; p2.skip = h1;
     const float *a1 = h1_tf32 ? h1_tf32 : h1;                 // GEMM operand; the skip path always reads fp32 h1
-    if (impl == GNNGLS_DENSE_TCGEN05) {
-        p1.round_tf32 = 1;
-        if (int rc = launch_tc_gemm<HID_, D_, EPI_FF1>(a1, W1, p1, st)) return rc;
-        return launch_tc_gemm<D_, HID_, EPI_FF2>(hid, W2, p2, st);
-    }
+    if (impl == GNNGLS_DENSE_TCGEN05) return launch_ff_fused(a1, W1, b1, W2, p2, st);
     if (impl == GNNGLS_DENSE_SIMT) {
         if (int rc = launch_simt_gemm<HID_, D_, EPI_FF1>(a1, W1, p1, st)) return rc;
         return launch_simt_gemm<D_, HID_, EPI_FF2>(hid, W2, p2, st);

@@ -39,6 +39,10 @@ __device__ __forceinline__ uint32_t tf32_bits(float x) {
     return r;
 }
 __device__ __forceinline__ float lrelu(float s) { return fmaxf(s, kSlope * s); }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float4 tf32_round4(float4 v) {
     return make_float4(__uint_as_float(tf32_bits(v.x)), __uint_as_float(tf32_bits(v.y)),
                        __uint_as_float(tf32_bits(v.z)), __uint_as_float(tf32_bits(v.w)));
@@ -190,61 +194,17 @@ struct StarCtx {
     const float *ELs, *ERs;
     int ksteps;
     float *pnum, *pden, *pmax;
-    int *arrive;          // [B*N*8] arrival counters (zeroed per launch)
-    const float *h, *bias, *bn_scale, *bn_shift;
-    float *h1, *h1_tf32;
 };
 
-// Finish one destination row for this warp's head.  The quad (4 lanes sharing g) owns the row:
-// lane t holds features {2t,2t+1} and {8+2t,9+2t} of the head.  Protocol (both stars of a
-// destination run it): publish my partial -> __threadfence -> bump the arrival counter; whoever
-// arrives second reads the other partial (L2, .cg), merges flash-style and applies
-// bias + skip + BatchNorm1.  No separate combine kernel, one partial read per destination.
-__device__ __forceinline__ void finish_row(const StarCtx &c, int j, float2 n0, float2 n1, float den, float mx) {
-    const bool live = (j < c.n) && (j != c.i);          // uniform across the quad
+// publish one destination row of this warp's head: lane t of the quad holds features {2t,2t+1} and
+// {8+2t,9+2t}.  (.cg stores: the partials are consumed by another SM through L2.)
+__device__ __forceinline__ void publish_row(const StarCtx &c, int j, float2 n0, float2 n1, float den, float mx) {
+    if (j >= c.n || j == c.i) return;
     const int64_t mine = ((int64_t)c.b * c.n + c.i) * c.n + j;
-    if (live) {
-        float *o = c.pnum + mine * D_ + c.hd * 16 + 2 * c.t;
-        __stcg(reinterpret_cast<float2 *>(o), n0);
-        __stcg(reinterpret_cast<float2 *>(o + 8), n1);
-        if (c.t == 0) { __stcg(c.pden + mine * H_ + c.hd, den); __stcg(c.pmax + mine * H_ + c.hd, mx); }
-    }
-    __threadfence();
-    __syncwarp();
-    const int64_t N = (int64_t)c.n * (c.n - 1) / 2;
-    const int64_t v = live ? (int64_t)c.b * N + kn_node(c.i, j, c.n) : 0;
-    int ticket = 0;
-    if (live && c.t == 0) ticket = atomicAdd(c.arrive + v * H_ + c.hd, 1);
-    ticket = __shfl_sync(0xffffffffu, ticket, (threadIdx.x & 31) & ~3);
-    if (!live || ticket == 0) return;                   // first to arrive: the other star finishes the row
-    __threadfence();
-    const int64_t other = ((int64_t)c.b * c.n + j) * c.n + c.i;
-    const float *po = c.pnum + other * D_ + c.hd * 16 + 2 * c.t;
-    const float2 q0 = __ldcg(reinterpret_cast<const float2 *>(po));
-    const float2 q1 = __ldcg(reinterpret_cast<const float2 *>(po + 8));
-    const float d2 = __ldcg(c.pden + other * H_ + c.hd), x2 = __ldcg(c.pmax + other * H_ + c.hd);
-    const float m = fmaxf(mx, x2);
-    const float s1 = ex2(mx - m), s2 = ex2(x2 - m);
-    const float inv = 1.f / fmaf(den, s1, d2 * s2);
-    const float a1 = s1 * inv, a2 = s2 * inv;
-    const int f0 = c.hd * 16 + 2 * c.t;
-#pragma unroll
-    for (int part = 0; part < 2; ++part) {
-        const int f = f0 + 8 * part;
-        const float2 mine2 = part ? n1 : n0, oth2 = part ? q1 : q0;
-        const float2 hv = *reinterpret_cast<const float2 *>(c.h + v * D_ + f);
-        const float2 sc = *reinterpret_cast<const float2 *>(c.bn_scale + f);
-        const float2 sh = *reinterpret_cast<const float2 *>(c.bn_shift + f);
-        float2 bb = make_float2(0.f, 0.f);
-        if (c.bias) bb = *reinterpret_cast<const float2 *>(c.bias + f);
-        float2 r;
-        r.x = (hv.x + (fmaf(mine2.x, a1, oth2.x * a2) + bb.x)) * sc.x + sh.x;
-        r.y = (hv.y + (fmaf(mine2.y, a1, oth2.y * a2) + bb.y)) * sc.y + sh.y;
-        *reinterpret_cast<float2 *>(c.h1 + v * D_ + f) = r;
-        if (c.h1_tf32)
-            *reinterpret_cast<float2 *>(c.h1_tf32 + v * D_ + f) =
-                make_float2(__uint_as_float(tf32_bits(r.x)), __uint_as_float(tf32_bits(r.y)));
-    }
+    float *o = c.pnum + mine * D_ + c.hd * 16 + 2 * c.t;
+    __stcg(reinterpret_cast<float2 *>(o), n0);
+    __stcg(reinterpret_cast<float2 *>(o + 8), n1);
+    if (c.t == 0) { __stcg(c.pden + mine * H_ + c.hd, den); __stcg(c.pmax + mine * H_ + c.hd, mx); }
 }
 
 // NT m-tiles (16 destinations each) processed together so that el and the B fragments of a k-step
@@ -297,8 +257,8 @@ __device__ __forceinline__ void star_tiles(const StarCtx &c, int mt0) {
 #pragma unroll
     for (int u = 0; u < NT; ++u) {
         const int j_lo = (mt0 + u) * 16 + c.g;
-        finish_row(c, j_lo, make_float2(acc0[u][0], acc0[u][1]), make_float2(acc1[u][0], acc1[u][1]), accs[u][0], mxa[u][0]);
-        finish_row(c, j_lo + 8, make_float2(acc0[u][2], acc0[u][3]), make_float2(acc1[u][2], acc1[u][3]), accs[u][2], mxa[u][1]);
+        publish_row(c, j_lo, make_float2(acc0[u][0], acc0[u][1]), make_float2(acc1[u][0], acc1[u][1]), accs[u][0], mxa[u][0]);
+        publish_row(c, j_lo + 8, make_float2(acc0[u][2], acc0[u][3]), make_float2(acc1[u][2], acc1[u][3]), accs[u][2], mxa[u][1]);
     }
 }
 
@@ -322,22 +282,35 @@ gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict_
     const int64_t node0 = (int64_t)b * N;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // ---- stage the star of vertex i: slot k <-> TSP edge {i,k}
-    for (int k = warp; k < KP; k += STAR_THREADS / 32) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool live = (k < n) && (k != i);
-        int64_t node = 0;
-        if (live) {
-            node = node0 + kn_node(i, k, n);
-            v = *reinterpret_cast<const float4 *>(ft + node * D_ + 4 * lane);
-        }
-        uint4 t;
-        t.x = tf32_bits(v.x); t.y = tf32_bits(v.y); t.z = tf32_bits(v.z); t.w = tf32_bits(v.w);
-        *reinterpret_cast<uint4 *>(Fs + (size_t)k * FS_LD + 4 * lane) = t;
-        if (lane < H_) ELs[k * H_ + lane] = live ? el[node * H_ + lane] * kLog2e : -INFINITY;
-        else if (lane < 2 * H_) ERs[k * H_ + (lane - H_)] = live ? er[node * H_ + (lane - H_)] * kLog2e : 0.f;
+    // ---- stage the star of vertex i (slot k <-> TSP edge {i,k}) with cp.async: every row of the star
+    // is in flight at once, so the CTA pays one L2 latency instead of one per row
+    for (int idx = threadIdx.x; idx < KP * 32; idx += STAR_THREADS) {
+        const int k = idx >> 5, q = idx & 31;                 // 16-byte piece q of row k
+        float *dst = Fs + (size_t)k * FS_LD + 4 * q;
+        if (k < n && k != i) cp_async16(dst, ft + (node0 + kn_node(i, k, n)) * D_ + 4 * q);
+        else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int idx = KP * H_ + threadIdx.x; idx < MP * H_; idx += STAR_THREADS) ERs[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < KP * 4; idx += STAR_THREADS) {
+        const int k = idx >> 2, q = idx & 3;                  // el row = 2 pieces, er row = 2 pieces
+        if (k < n && k != i) {
+            const int64_t node = node0 + kn_node(i, k, n);
+            if (q < 2) cp_async16(ELs + k * H_ + 4 * q, el + node * H_ + 4 * q);
+            else cp_async16(ERs + k * H_ + 4 * (q - 2), er + node * H_ + 4 * (q - 2));
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // in place: ft -> TF32 (round to nearest; the tensor core would otherwise truncate), el/er -> log2 domain
+    for (int idx = threadIdx.x; idx < KP * 32; idx += STAR_THREADS) {
+        float4 *ptr = reinterpret_cast<float4 *>(Fs + (size_t)(idx >> 5) * FS_LD + 4 * (idx & 31));
+        *ptr = tf32_round4(*ptr);
+    }
+    for (int idx = threadIdx.x; idx < MP * H_; idx += STAR_THREADS) {
+        const int k = idx >> 3;
+        const bool live = (k < n) && (k != i);
+        if (idx < KP * H_) ELs[idx] = live ? ELs[idx] * kLog2e : -INFINITY;
+        ERs[idx] = live ? ERs[idx] * kLog2e : 0.f;
+    }
     __syncthreads();
 
     // ---- per-head top-2 of el over the star (warp w <-> head w)
@@ -365,12 +338,78 @@ gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict_
     c.n = n; c.i = i; c.b = b; c.hd = warp; c.g = lane >> 2; c.t = lane & 3;
     c.m1 = TM1[warp]; c.m2 = TM2[warp]; c.a1 = TA1[warp];
     c.Fh = Fs + warp * 16; c.ELs = ELs; c.ERs = ERs; c.ksteps = KP / 8;
-    c.pnum = pnum; c.pden = pden; c.pmax = pmax; c.arrive = arrive;
-    c.h = h; c.bias = bias; c.bn_scale = bn_scale; c.bn_shift = bn_shift; c.h1 = h1; c.h1_tf32 = h1_tf32;
+    c.pnum = pnum; c.pden = pden; c.pmax = pmax;
     const int MT = MP / 16;
     int mt = 0;
     for (; mt + 2 <= MT; mt += 2) star_tiles<2>(c, mt);
     if (mt < MT) star_tiles<1>(c, mt);
+
+    // ---- every destination {i,j} belongs to the stars of i and of j.  Publish this star's partials,
+    // then bump the destination's arrival counter: the star that arrives second merges the two
+    // partials (flash-style rescale, always in (min(i,j), max(i,j)) order so the result does not
+    // depend on arrival order) and applies bias + skip + BatchNorm1.  No separate combine pass.
+    __threadfence();
+    __syncthreads();
+    int *second = reinterpret_cast<int *>(ELs);               // reuse: [n] flags
+    for (int j = threadIdx.x; j < n; j += STAR_THREADS)
+        second[j] = (j != i) ? atomicAdd(arrive + node0 + kn_node(i, j, n), 1) : 0;
+    __syncthreads();
+    __threadfence();
+    const int hh = lane >> 2;
+    const float4 sc = *reinterpret_cast<const float4 *>(bn_scale + 4 * lane);
+    const float4 sh = *reinterpret_cast<const float4 *>(bn_shift + 4 * lane);
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bb = *reinterpret_cast<const float4 *>(bias + 4 * lane);
+    // compact the destinations this CTA must finish, then two per warp iteration (more loads in flight)
+    int *todo = second + round_up(n, 4);                      // [n] compacted list, count in todo[n]
+    __syncthreads();
+    if (warp == 0) {
+        int cnt = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int j = base + lane;
+            const bool f = j < n && second[j] != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            if (f) todo[cnt + __popc(m & ((1u << lane) - 1))] = j;
+            cnt += __popc(m);
+        }
+        if (lane == 0) todo[n] = cnt;
+    }
+    __syncthreads();
+    const int cnt = todo[n];
+    for (int q0 = warp * 2; q0 < cnt; q0 += (STAR_THREADS / 32) * 2) {
+        float4 n1[2], n2[2], hv[2];
+        float x1[2], x2[2], d1[2], d2[2];
+        int64_t v[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            ok[u] = q0 + u < cnt;
+            const int j = todo[ok[u] ? q0 + u : q0];
+            const int lo = i < j ? i : j, hi = i < j ? j : i;
+            const int64_t p1 = ((int64_t)b * n + lo) * n + hi, p2 = ((int64_t)b * n + hi) * n + lo;
+            v[u] = node0 + kn_node(lo, hi, n);
+            n1[u] = __ldcg(reinterpret_cast<const float4 *>(pnum + p1 * D_ + 4 * lane));
+            n2[u] = __ldcg(reinterpret_cast<const float4 *>(pnum + p2 * D_ + 4 * lane));
+            x1[u] = __ldcg(pmax + p1 * H_ + hh); x2[u] = __ldcg(pmax + p2 * H_ + hh);
+            d1[u] = __ldcg(pden + p1 * H_ + hh); d2[u] = __ldcg(pden + p2 * H_ + hh);
+            hv[u] = *reinterpret_cast<const float4 *>(h + v[u] * D_ + 4 * lane);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!ok[u]) continue;
+            const float mx = fmaxf(x1[u], x2[u]);
+            const float s1 = ex2(x1[u] - mx), s2 = ex2(x2[u] - mx);
+            const float inv = 1.f / fmaf(d1[u], s1, d2[u] * s2);
+            const float a1 = s1 * inv, a2 = s2 * inv;
+            float4 o;
+            o.x = (hv[u].x + (fmaf(n1[u].x, a1, n2[u].x * a2) + bb.x)) * sc.x + sh.x;
+            o.y = (hv[u].y + (fmaf(n1[u].y, a1, n2[u].y * a2) + bb.y)) * sc.y + sh.y;
+            o.z = (hv[u].z + (fmaf(n1[u].z, a1, n2[u].z * a2) + bb.z)) * sc.z + sh.z;
+            o.w = (hv[u].w + (fmaf(n1[u].w, a1, n2[u].w * a2) + bb.w)) * sc.w + sh.w;
+            *reinterpret_cast<float4 *>(h1 + v[u] * D_ + 4 * lane) = o;
+            if (h1_tf32) *reinterpret_cast<float4 *>(h1_tf32 + v[u] * D_ + 4 * lane) = tf32_round4(o);
+        }
+    }
 }
 
 }  // namespace
@@ -393,7 +432,7 @@ extern "C" int gnngls_gat_aggregate_csr(const int32_t *indptr, const int32_t *in
 extern "C" size_t gnngls_gat_kn_workspace_bytes(int B, int n) {
     if (B <= 0 || n <= 0) return 0;
     const size_t N = (size_t)n * (n - 1) / 2;
-    return sizeof(float) * (size_t)B * n * n * (D_ + 2 * H_) + sizeof(int) * (size_t)B * N * H_;
+    return sizeof(float) * (size_t)B * n * n * (D_ + 2 * H_) + sizeof(int) * (size_t)B * N;
 }
 
 extern "C" int gnngls_gat_aggregate_kn(int B, int n, const float *ft, const float *el, const float *er,
@@ -415,7 +454,7 @@ extern "C" int gnngls_gat_aggregate_kn(int B, int n, const float *ft, const floa
     float *pden = pnum + (size_t)B * n * n * D_;
     float *pmax = pden + (size_t)B * n * n * H_;
     int *arrive = reinterpret_cast<int *>(pmax + (size_t)B * n * n * H_);
-    GNNGLS_CUDA_OK(cudaMemsetAsync(arrive, 0, sizeof(int) * (size_t)B * N * H_, st));
+    GNNGLS_CUDA_OK(cudaMemsetAsync(arrive, 0, sizeof(int) * (size_t)B * N, st));
     if (smem > 48 * 1024)
         GNNGLS_CUDA_OK(cudaFuncSetAttribute(gat_kn_star_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gat_kn_star_kernel<<<B * n, STAR_THREADS, smem, st>>>(n, ft, el, er, pnum, pden, pmax, arrive, h, gat_bias,
