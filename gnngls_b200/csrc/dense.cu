@@ -91,11 +91,44 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams &p, int64_t row, i
     }
 }
 
-// Thread-per-row epilogue of the tensor-core GEMM: this thread owns 32 consecutive accumulator
-// columns [col, col+32) of `row` (straight out of tcgen05.ld), `sv` are the per-column vectors
-// staged in shared memory (FC: attn_l|attn_r; FF1: b1; FF2: b2|bn_scale|bn_shift).
+// ------------------------------------------------------------------------------------------------
+// Warp-private 32x32 fp32 staging tile (4 KB, 128-byte rows, 16-byte pieces XOR-swizzled by row&7):
+// thread-per-row accesses (what tcgen05.ld produces) and 4-rows-per-instruction coalesced accesses
+// are both bank-conflict free, so global memory is only ever touched with full 128-byte lines.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 *stg_slot(float *stg, int row, int piece) {
+    return reinterpret_cast<float4 *>(stg + row * 32 + ((piece ^ (row & 7)) << 2));
+}
+// coalesced global -> staging: 32 rows x 32 columns starting at (row0, col0) of a row-major [M, ld] matrix
+__device__ __forceinline__ void stg_load_tile(float *stg, const float *src, int64_t row0, int col0, int ld, int64_t M, int lane) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), pc = lane & 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < M) v = *reinterpret_cast<const float4 *>(src + (row0 + r) * ld + col0 + 4 * pc);
+        *stg_slot(stg, r, pc) = v;
+    }
+}
+// staging -> coalesced global (optionally a second, TF32-rounded copy)
+__device__ __forceinline__ void stg_store_tile(const float *stg, float *dst, float *dst_tf32, int64_t row0, int col0, int ld,
+                                               int64_t M, int lane) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), pc = lane & 7;
+        if (row0 + r < M) {
+            const float4 v = *stg_slot(const_cast<float *>(stg), r, pc);
+            *reinterpret_cast<float4 *>(dst + (row0 + r) * ld + col0 + 4 * pc) = v;
+            if (dst_tf32) *reinterpret_cast<float4 *>(dst_tf32 + (row0 + r) * ld + col0 + 4 * pc) = tf32_rna4(v);
+        }
+    }
+}
+
+// Tensor-core epilogue for 32 accumulator columns [col, col+32) of the 32 rows starting at row0 that
+// this warp owns (thread == row out of tcgen05.ld), through the warp's staging tile.
 template <int EPI>
-__device__ __forceinline__ void epilogue_row32(const EpiParams &p, const float *sv, int64_t row, int col, float (&v)[32]) {
+__device__ __forceinline__ void epilogue_tile32(const EpiParams &p, const float *sv, float *stg, int64_t row0, int col,
+                                                float (&v)[32], int lane) {
+    const int64_t row = row0 + lane;
     if (EPI == EPI_FC) {
         float sl[2] = {0.f, 0.f}, sr[2] = {0.f, 0.f};       // 32 columns = two heads of 16
 #pragma unroll
@@ -104,14 +137,16 @@ __device__ __forceinline__ void epilogue_row32(const EpiParams &p, const float *
             const float4 ar = *reinterpret_cast<const float4 *>(sv + D_ + col + 4 * j);
             sl[j >> 2] += v[4 * j] * al.x + v[4 * j + 1] * al.y + v[4 * j + 2] * al.z + v[4 * j + 3] * al.w;
             sr[j >> 2] += v[4 * j] * ar.x + v[4 * j + 1] * ar.y + v[4 * j + 2] * ar.z + v[4 * j + 3] * ar.w;
+            *stg_slot(stg, lane, j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        float *o = p.out + row * D_ + col;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4 *>(o + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        *reinterpret_cast<float2 *>(p.el + row * H_ + (col >> 4)) = make_float2(sl[0], sl[1]);
-        *reinterpret_cast<float2 *>(p.er + row * H_ + (col >> 4)) = make_float2(sr[0], sr[1]);
+        if (row < p.M) {
+            *reinterpret_cast<float2 *>(p.el + row * H_ + (col >> 4)) = make_float2(sl[0], sl[1]);
+            *reinterpret_cast<float2 *>(p.er + row * H_ + (col >> 4)) = make_float2(sr[0], sr[1]);
+        }
+        __syncwarp();
+        stg_store_tile(stg, p.out, nullptr, row0, col, D_, p.M, lane);
+        __syncwarp();
     } else if (EPI == EPI_FF1) {
-        float *o = p.out + row * HID_ + col;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 b = *reinterpret_cast<const float4 *>(sv + col + 4 * j);
@@ -119,26 +154,28 @@ __device__ __forceinline__ void epilogue_row32(const EpiParams &p, const float *
             r.x = fmaxf(v[4 * j] + b.x, 0.f); r.y = fmaxf(v[4 * j + 1] + b.y, 0.f);
             r.z = fmaxf(v[4 * j + 2] + b.z, 0.f); r.w = fmaxf(v[4 * j + 3] + b.w, 0.f);
             if (p.round_tf32) r = tf32_rna4(r);
-            *reinterpret_cast<float4 *>(o + 4 * j) = r;
+            *stg_slot(stg, lane, j) = r;
         }
+        __syncwarp();
+        stg_store_tile(stg, p.out, nullptr, row0, col, HID_, p.M, lane);
+        __syncwarp();
     } else {
-        const float *sk = p.skip + row * D_ + col;
-        float4 s[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s[j] = *reinterpret_cast<const float4 *>(sk + 4 * j);
-        float *o = p.out + row * D_ + col;
-        float *ot = p.out_tf32 ? p.out_tf32 + row * D_ + col : nullptr;
+        stg_load_tile(stg, p.skip, row0, col, D_, p.M, lane);          // skip connection (fp32 h1), coalesced
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+            const float4 s = *stg_slot(stg, lane, j);
             const float4 b = *reinterpret_cast<const float4 *>(sv + col + 4 * j);
             const float4 sc = *reinterpret_cast<const float4 *>(sv + D_ + col + 4 * j);
             const float4 sh = *reinterpret_cast<const float4 *>(sv + 2 * D_ + col + 4 * j);
             float4 r;
-            r.x = (s[j].x + (v[4 * j] + b.x)) * sc.x + sh.x; r.y = (s[j].y + (v[4 * j + 1] + b.y)) * sc.y + sh.y;
-            r.z = (s[j].z + (v[4 * j + 2] + b.z)) * sc.z + sh.z; r.w = (s[j].w + (v[4 * j + 3] + b.w)) * sc.w + sh.w;
-            *reinterpret_cast<float4 *>(o + 4 * j) = r;
-            if (ot) *reinterpret_cast<float4 *>(ot + 4 * j) = tf32_rna4(r);
+            r.x = (s.x + (v[4 * j] + b.x)) * sc.x + sh.x; r.y = (s.y + (v[4 * j + 1] + b.y)) * sc.y + sh.y;
+            r.z = (s.z + (v[4 * j + 2] + b.z)) * sc.z + sh.z; r.w = (s.w + (v[4 * j + 3] + b.w)) * sc.w + sh.w;
+            *stg_slot(stg, lane, j) = r;
         }
+        __syncwarp();
+        stg_store_tile(stg, p.out, p.out_tf32, row0, col, D_, p.M, lane);
+        __syncwarp();
     }
 }
 
@@ -166,6 +203,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra.uni WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one lane of a converged warp (lets the compiler keep MMA operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -244,13 +292,14 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 // tcgen05 GEMM:  C[M, N_TOTAL] = A[M, K_TOTAL] * W[N_TOTAL, K_TOTAL]^T  with fused epilogue
 // ================================================================================================
 constexpr int BM = 128, BN = 128, BK = 32;           // BK fp32 = 128 bytes = one swizzle row
-constexpr int STAGES = 6;
+constexpr int STAGES = 5;
 constexpr int STAGE_BYTES = (BM + BN) * BK * 4;      // 32 KB
 constexpr int EPI_WARPS = 8;                         // two per TMEM lane quarter, 64 columns each
 constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;   // warp0 TMA, warp1 MMA/TMEM, warps 2..9 epilogue
 constexpr int TMEM_COLS = 256;                       // two 128-column fp32 accumulators
 constexpr int SVEC_FLOATS = 512;                     // per-column epilogue vectors staged in smem
-constexpr size_t GEMM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + SVEC_FLOATS * 4 + 256;
+constexpr int STG_TILE_BYTES = 32 * 32 * 4;              // per-warp epilogue staging tile
+constexpr size_t GEMM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_WARPS * STG_TILE_BYTES + SVEC_FLOATS * 4 + 256;
 
 template <int N_TOTAL, int K_TOTAL, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -258,10 +307,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int KB = K_TOTAL / BK;
     constexpr int NB = N_TOTAL / BN;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024B-aligned, still .shared
     unsigned char *stage_base = smem;
-    float *svec = reinterpret_cast<float *>(smem + (size_t)STAGES * STAGE_BYTES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES + SVEC_FLOATS * 4);
+    float *staging = reinterpret_cast<float *>(smem + (size_t)STAGES * STAGE_BYTES);
+    float *svec = staging + EPI_WARPS * (STG_TILE_BYTES / 4);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(svec + SVEC_FLOATS);
     uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
 
@@ -307,39 +357,40 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+        // ------------------------------------------------------------------ MMA issuer (warp-uniform control flow)
+        constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
-                    const uint64_t da = make_sw128_kmajor_desc(sa);
-                    const uint64_t db = make_sw128_kmajor_desc(sa + BM * BK * 4);
+                const uint32_t sa = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
+                const uint64_t da = make_sw128_kmajor_desc(sa);
+                const uint64_t db = make_sw128_kmajor_desc(sa + BM * BK * 4);
+                if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {      // UMMA_K = 8 for tf32: 32 bytes along K
+                    for (int k = 0; k < BK / 8; ++k)         // UMMA_K = 8 for tf32: 32 bytes along K
                         umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                    }
                     umma_commit(&empty[stage]);              // frees the smem slot when these MMAs finish
                     if (kb == KB - 1) umma_commit(&tfull[acc]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ------------------------------------------------------------------ epilogue warps
         const int q = warp & 3;                               // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;                     // which 64 accumulator columns
+        float *stg = staging + (warp - 2) * (STG_TILE_BYTES / 4);
         uint32_t acc = 0, acc_phase = 0;
         for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int m_blk = (int)(w / NB), n_blk = (int)(w % NB);
-            const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
+            const int64_t row0 = (int64_t)m_blk * BM + q * 32;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -347,7 +398,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int col_in_tile = half * 64 + c * 32;
                 float v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + col_in_tile, v);
-                if (row < p.M) epilogue_row32<EPI>(p, svec, row, n_blk * BN + col_in_tile, v);
+                epilogue_tile32<EPI>(p, svec, stg, row0, n_blk * BN + col_in_tile, v, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -429,25 +480,26 @@ int launch_tc_gemm(const float *A, const float *W, const EpiParams &p, cudaStrea
 // ================================================================================================
 constexpr int FF_HC = 32;                              // hidden units per chunk
 constexpr int FF_CHUNKS = HID_ / FF_HC;                // 16
-constexpr int FF_WSTAGES = 6;
+constexpr int FF_WSTAGES = 5;
 constexpr int FF_WSTAGE_BYTES = 16384;                 // W1c: 4 boxes [32 x 32]; W2c: 1 box [128 x 32]
 constexpr int FF_A_BYTES = BM * D_ * 4;                // 64 KB: 4 boxes [128 x 32]
 constexpr int FF_H_BYTES = BM * FF_HC * 4;             // 16 KB per buffer
 constexpr int FF_SVEC = 3 * D_ + HID_;                 // b2 | bn_scale | bn_shift | b1
 constexpr int FF_THREADS = 11 * 32;                    // warp0 W-TMA, warp1 MMA, warps 2..9 epilogue, warp10 A-TMA
 constexpr int FF_NBARS = 2 + 2 * FF_WSTAGES + 8 + 2;
-constexpr size_t FF_SMEM = 1024 + FF_A_BYTES + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES + 2 * FF_H_BYTES + FF_SVEC * 4 +
-                           FF_NBARS * 8 + 16;
+constexpr size_t FF_SMEM = 1024 + FF_A_BYTES + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES + 2 * FF_H_BYTES +
+                           EPI_WARPS * STG_TILE_BYTES + FF_SVEC * 4 + FF_NBARS * 8 + 16;
 
 __global__ void __launch_bounds__(FF_THREADS, 1)
 ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const EpiParams p, const float *__restrict__ b1) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024B-aligned, still .shared
     unsigned char *sA = smem;
     unsigned char *sW = sA + FF_A_BYTES;
     unsigned char *sH = sW + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES;
-    float *svec = reinterpret_cast<float *>(sH + 2 * FF_H_BYTES);
+    float *staging = reinterpret_cast<float *>(sH + 2 * FF_H_BYTES);
+    float *svec = staging + EPI_WARPS * (STG_TILE_BYTES / 4);
     uint64_t *bars = reinterpret_cast<uint64_t *>(svec + FF_SVEC);
     uint64_t *a_full = bars, *a_empty = bars + 1, *w_full = bars + 2, *w_empty = w_full + FF_WSTAGES;
     uint64_t *d1_full = w_empty + FF_WSTAGES, *d1_empty = d1_full + 2, *h_full = d1_empty + 2, *h_empty = h_full + 2;
@@ -513,33 +565,36 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc1 = make_idesc_tf32(BM, FF_HC), idesc2 = make_idesc_tf32(BM, BN);
-            uint32_t stage = 0, phase = 0, it = 0;
-            uint32_t n_d1[2] = {0, 0}, n_h[2] = {0, 0};
-            const uint32_t aA = smem_u32(sA);
-            auto gemm2 = [&](int c) {
-                const int g = c & 1;
-                mbar_wait(&h_full[g], n_h[g] & 1); ++n_h[g];          // epilogue-1 has written Hc[g]
-                mbar_wait(&w_full[stage], phase);
-                tc_fence_after();
-                const uint64_t da = make_sw128_kmajor_desc(smem_u32(sH + g * FF_H_BYTES));
-                const uint64_t db = make_sw128_kmajor_desc(smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES));
+        // ------------------------------------------------------------------ MMA issuer (warp-uniform control flow)
+        constexpr uint32_t idesc1 = make_idesc_tf32(BM, FF_HC), idesc2 = make_idesc_tf32(BM, BN);
+        uint32_t stage = 0, phase = 0, it = 0;
+        uint32_t n_d1[2] = {0, 0}, n_h[2] = {0, 0};
+        const uint32_t aA = smem_u32(sA);
+        auto gemm2 = [&](int c) {
+            const int g = c & 1;
+            mbar_wait(&h_full[g], n_h[g] & 1); ++n_h[g];          // epilogue-1 has written Hc[g]
+            mbar_wait(&w_full[stage], phase);
+            tc_fence_after();
+            const uint64_t da = make_sw128_kmajor_desc(smem_u32(sH + g * FF_H_BYTES));
+            const uint64_t db = make_sw128_kmajor_desc(smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES));
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < FF_HC / 8; ++k) umma_tf32(tm_d2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (c | k) != 0);
                 umma_commit(&w_empty[stage]);
                 umma_commit(&h_empty[g]);
-                if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
-            };
-            for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
-                mbar_wait(a_full, it & 1);
-                for (int c = 0; c < FF_CHUNKS; ++c) {
-                    const int g = c & 1;
-                    mbar_wait(&d1_empty[g], (n_d1[g] & 1) ^ 1); ++n_d1[g];   // epilogue-1 drained D1[g]
-                    mbar_wait(&w_full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sw = smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES);
+            }
+            __syncwarp();
+            if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+        };
+        for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
+            mbar_wait(a_full, it & 1);
+            for (int c = 0; c < FF_CHUNKS; ++c) {
+                const int g = c & 1;
+                mbar_wait(&d1_empty[g], (n_d1[g] & 1) ^ 1); ++n_d1[g];   // epilogue-1 drained D1[g]
+                mbar_wait(&w_full[stage], phase);
+                tc_fence_after();
+                const uint32_t sw = smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES);
+                if (elect_one()) {
 #pragma unroll
                     for (int kb = 0; kb < D_ / BK; ++kb) {
                         const uint64_t da = make_sw128_kmajor_desc(aA + kb * (BM * BK * 4));
@@ -551,13 +606,15 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     umma_commit(&w_empty[stage]);
                     umma_commit(&d1_full[g]);
                     if (c == FF_CHUNKS - 1) umma_commit(a_empty);     // last reader of the A tile
-                    if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
-                    if (c == 1) { mbar_wait(d2_empty, (it & 1) ^ 1); tc_fence_after(); }   // before GEMM2(0) overwrites D2
-                    if (c >= 1) gemm2(c - 1);
                 }
-                gemm2(FF_CHUNKS - 1);
-                umma_commit(d2_full);
+                __syncwarp();
+                if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                if (c == 1) { mbar_wait(d2_empty, (it & 1) ^ 1); tc_fence_after(); }   // before GEMM2(0) overwrites D2
+                if (c >= 1) gemm2(c - 1);
             }
+            gemm2(FF_CHUNKS - 1);
+            if (elect_one()) umma_commit(d2_full);
+            __syncwarp();
         }
     } else {
         // ------------------------------------------------------------------ epilogue warps
@@ -566,6 +623,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int r_in_tile = q * 32 + lane;
         uint32_t n_e1 = 0, it = 0;
         unsigned char *hrow = sH + g * FF_H_BYTES + r_in_tile * 128;
+        float *stg = staging + (warp - 2) * (STG_TILE_BYTES / 4);
         for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
             for (int c = g; c < FF_CHUNKS; c += 2, ++n_e1) {
                 mbar_wait(&d1_full[g], n_e1 & 1);
@@ -577,12 +635,14 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (lane == 0) mbar_arrive(&d1_empty[g]);     // D1[g] is in registers now
                 mbar_wait(&h_empty[g], (n_e1 & 1) ^ 1);       // GEMM2 of chunk c-2 has finished reading Hc[g]
                 const float *bb = svec + 3 * D_ + c * FF_HC;
+                float4 bias[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bias[j] = *reinterpret_cast<const float4 *>(bb + 4 * j);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {                 // 16-byte piece j of this row, 128B swizzle
-                    const float4 b = *reinterpret_cast<const float4 *>(bb + 4 * j);
                     float4 r;
-                    r.x = tf32_rna(fmaxf(v[4 * j] + b.x, 0.f)); r.y = tf32_rna(fmaxf(v[4 * j + 1] + b.y, 0.f));
-                    r.z = tf32_rna(fmaxf(v[4 * j + 2] + b.z, 0.f)); r.w = tf32_rna(fmaxf(v[4 * j + 3] + b.w, 0.f));
+                    r.x = tf32_rna(fmaxf(v[4 * j] + bias[j].x, 0.f)); r.y = tf32_rna(fmaxf(v[4 * j + 1] + bias[j].y, 0.f));
+                    r.z = tf32_rna(fmaxf(v[4 * j + 2] + bias[j].z, 0.f)); r.w = tf32_rna(fmaxf(v[4 * j + 3] + bias[j].w, 0.f));
                     *reinterpret_cast<float4 *>(hrow + ((j ^ (r_in_tile & 7)) << 4)) = r;
                 }
                 fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core
@@ -590,7 +650,6 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (lane == 0) mbar_arrive(&h_full[g]);
             }
             // final epilogue: this group owns 64 of the 128 output columns
-            const int64_t row = w * BM + r_in_tile;
             mbar_wait(d2_full, it & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -598,7 +657,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int col = g * 64 + c2 * 32;
                 float v[32];
                 tmem_ld_32x32(tm_d2 + ((uint32_t)(q * 32) << 16) + col, v);
-                if (row < p.M) epilogue_row32<EPI_FF2>(p, svec, row, col, v);
+                epilogue_tile32<EPI_FF2>(p, svec, stg, w * BM + q * 32, col, v, lane);
             }
             tc_fence_before();
             __syncwarp();
