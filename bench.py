@@ -33,15 +33,16 @@ UNIT = 'instances/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--n', type=int, default=100, help='cities per instance')
-    ap.add_argument('--instances-per-gpu', type=int, default=4096)
+    ap.add_argument('--instances-per-gpu', type=int, default=12500,
+                    help='shard per GPU; 12,500 x 8 GPUs = the 100k-instance TSP100 config of BASELINE.json')
     ap.add_argument('--gls-iters', type=int, default=10, help='GLS outer iterations K (fixed count, SURVEY 8(d))')
     ap.add_argument('--perturbation-moves', type=int, default=20)
-    ap.add_argument('--micro-batch', type=int, default=32)
-    ap.add_argument('--chunk', type=int, default=1024, help='instances per host->device chunk in the e2e path')
+    ap.add_argument('--micro-batch', type=int, default=64)
+    ap.add_argument('--chunk', type=int, default=2048, help='instances per host->device chunk in the e2e path')
     ap.add_argument('--cpu-sample', type=int, default=4, help='instances in the bounded CPU-baseline sample')
     ap.add_argument('--ref-sample', type=int, default=2, help='instances per step of the reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -221,8 +222,12 @@ def main():
     model, weights = make_model(dev)
     solver = pipeline.RegretGLS(model, micro_batch=args.micro_batch)
     S, n = args.instances_per_gpu, args.n
-    _, D_np = instances.random_instances(S, n, seed=instances.DEFAULT_SEED + rank)
-    D_host = torch.from_numpy(D_np).pin_memory()
+    D_host = torch.empty(S, n, n, dtype=torch.float64).pin_memory()
+    rng = np.random.default_rng(instances.DEFAULT_SEED + rank)
+    for b0 in range(0, S, 2048):                     # chunked: the temporaries of distance_matrices are 3x the chunk
+        b1 = min(S, b0 + 2048)
+        D_host[b0:b1] = torch.from_numpy(instances.distance_matrices(rng.random((b1 - b0, n, 2))))
+    D_np = D_host.numpy()
     D_dev = D_host.to(dev)
     if weights.startswith('random-init'):
         # untrained weights give near-constant raw outputs: calibrate the synthetic regret scaler once so the
@@ -230,14 +235,12 @@ def main():
         _, D_cal = instances.random_instances(min(S, args.micro_batch), n, seed=instances.DEFAULT_SEED - 1)
         solver.calibrate_synthetic_regret_scaler(torch.from_numpy(D_cal).to(dev))
     kw = dict(n_iters=args.gls_iters, perturbation_moves=args.perturbation_moves)
-    g_tours = torch.empty(world * S, n + 1, dtype=torch.int32, device=dev) if world > 1 else None
-    g_costs = torch.empty(world * S, dtype=torch.float64, device=dev) if world > 1 else None
+    from gnngls_b200 import distributed as gd
 
     def step_resident():
         res = solver.solve(D_dev, **kw)
-        if world > 1:       # the only collective: final result gather over NCCL/NVLink
-            dist.all_gather_into_tensor(g_tours, res.best_tours)
-            dist.all_gather_into_tensor(g_costs, res.best_costs)
+        # the only collective: final gather of tours/costs over NCCL/NVLink (no-op for one rank)
+        gd.gather_results(res.best_tours, res.best_costs, world * S)
         return res
 
     def barrier():
@@ -302,13 +305,20 @@ def main():
         # every timed call covers <= micro_batch instances; total instance-layers = steps * S * 8
         total_bytes = alg_bytes_per_instance_layer * S * 8 * args.steps
         achieved = total_bytes / (gat_ms / 1e3) / 1e9
-        roof = {'kernel': 'gat_kn_star_kernel + gat_kn_combine_kernel (one aggregate launch pair per layer)',
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'gat_kn_star_traffic.json')      # from the committed ncu --set full capture
+        if os.path.exists(tp):
+            traffic = json.load(open(tp))['dram_bytes_per_instance_layer'] * per_call_instances
+        roof = {'kernel': 'gat_kn_star_kernel (K_n edge-softmax/aggregate + skip + BN1, one launch per layer and micro-batch)',
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_source': peak_src,
+                'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes_per_instance_layer * per_call_instances,
                 'avg_launch_ms': gat_ms / gat_calls, 'launches_timed': gat_calls,
-                'note': 'algorithmic gather bytes (544 B/edge); the star kernel serves them from shared memory after '
-                        'reading each ft row twice, so frac > 1 is reuse, not skipped work (see DESIGN.md)'}
+                'compulsory_hbm_gbs': (N_nodes * (2 * 512 + 2 * 64 + 512 + 2 * 512) * S * 8 * args.steps) / (gat_ms / 1e3) / 1e9,
+                'note': 'achieved = ALGORITHMIC gather bytes of SURVEY 8(d) (544 B/edge + 544 B/node) / kernel time. The '
+                        'star kernel stages each ft row in shared memory once per incident vertex (2 reads per row) and '
+                        'serves the 2(n-2)=196-fold logical re-reads from SMEM/registers, so frac > 1 measures reuse, not '
+                        'skipped work; `traffic` is the real DRAM traffic per launch from ncu (DESIGN.md section 5).'}
     total_stage = sum(v[0] for v in stages.values())
     stage_ms = {k: round(v[0] / args.steps, 3) for k, v in stages.items()}
     cand_2opt, cand_rel = (n - 2) * (n - 3) // 2, (n - 2) ** 2

@@ -360,7 +360,7 @@ gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict_
     const float4 sh = *reinterpret_cast<const float4 *>(bn_shift + 4 * lane);
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias) bb = *reinterpret_cast<const float4 *>(bias + 4 * lane);
-    // compact the destinations this CTA must finish, then two per warp iteration (more loads in flight)
+    // compact the destinations this CTA must finish, then FIN_U per warp iteration (more loads in flight)
     int *todo = second + round_up(n, 4);                      // [n] compacted list, count in todo[n]
     __syncthreads();
     if (warp == 0) {
@@ -376,13 +376,14 @@ gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict_
     }
     __syncthreads();
     const int cnt = todo[n];
-    for (int q0 = warp * 2; q0 < cnt; q0 += (STAR_THREADS / 32) * 2) {
-        float4 n1[2], n2[2], hv[2];
-        float x1[2], x2[2], d1[2], d2[2];
-        int64_t v[2];
-        bool ok[2];
+    constexpr int FIN_U = 3;
+    for (int q0 = warp * FIN_U; q0 < cnt; q0 += (STAR_THREADS / 32) * FIN_U) {
+        float4 n1[FIN_U], n2[FIN_U], hv[FIN_U];
+        float x1[FIN_U], x2[FIN_U], d1[FIN_U], d2[FIN_U];
+        int64_t v[FIN_U];
+        bool ok[FIN_U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < FIN_U; ++u) {
             ok[u] = q0 + u < cnt;
             const int j = todo[ok[u] ? q0 + u : q0];
             const int lo = i < j ? i : j, hi = i < j ? j : i;
@@ -395,7 +396,7 @@ gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict_
             hv[u] = *reinterpret_cast<const float4 *>(h + v[u] * D_ + 4 * lane);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < FIN_U; ++u) {
             if (!ok[u]) continue;
             const float mx = fmaxf(x1[u], x2[u]);
             const float s1 = ex2(x1[u] - mx), s2 = ex2(x2[u] - mx);
