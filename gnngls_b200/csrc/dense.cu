@@ -467,28 +467,60 @@ int launch_tc_gemm(const float *A, const float *W, const EpiParams &p, cudaStrea
 // ================================================================================================
 // Fused feed-forward block on tcgen05:  h_out = BN2(h1 + relu(h1 W1^T + b1) W2^T + b2)
 //
-// One persistent CTA per 128-row tile; the 128x512 hidden activation never leaves the SM:
-//   * the A tile (TF32 copy of h1, 64 KB) stays resident in shared memory for the whole tile;
-//   * W1 / W2 stream through a 6-stage TMA ring in chunks of 32 hidden units (16 KB per stage);
-//   * GEMM1(c): D1[c&1] (TMEM, 32 cols) = A . W1c^T            (16 x tcgen05.mma 128x32x8)
-//   * epilogue-1 (4 warps per chunk parity): tcgen05.ld -> +b1, ReLU, cvt.rna.tf32 -> written to
-//     shared memory in the 128B-swizzled K-major layout the tensor core expects (hidden chunk as
-//     the A operand of the second contraction), fence.proxy.async, mbarrier to the MMA thread;
-//   * GEMM2(c): D2 (TMEM, 128 cols) += Hc . W2c^T               (4 x tcgen05.mma 128x128x8)
-//   * final epilogue (8 warps): tcgen05.ld D2 -> +b2 + skip(h1 fp32) -> BN2 -> h_out (+ TF32 copy).
-// The MMA thread issues GEMM1(c+1) before GEMM2(c) so the tensor core works while epilogue-1 runs.
+// One persistent CTA per 128-row tile; the 128x512 hidden activation never leaves the SM and BOTH
+// left-hand operands live in tensor memory, so shared memory only carries the streamed weights:
+//   * A tile (TF32 copy of h1): TMA -> smem (64 KB) -> four "stager" warps copy it into TMEM
+//     (tcgen05.st, lane = row, column = k); the smem buffer is released at once, so the next tile's
+//     TMA overlaps the whole tile.  Re-reading A from smem for each of the 16 hidden chunks was the
+//     shared-memory-port bottleneck of the first version (tools/umma_bench.cu: 40 cycles per N=32 MMA).
+//   * W1 / W2 stream through a TMA ring in chunks of 32 hidden units (16 KB per stage);
+//   * GEMM1(c): D1[c&1] (TMEM, 32 cols) = A[tmem] . W1c^T        (16 x tcgen05.mma 128x32x8, A from TMEM)
+//   * epilogue-1 (4 warps per chunk parity): tcgen05.ld -> +b1, ReLU, cvt.rna.tf32 -> tcgen05.st into
+//     H[c&1] (TMEM, 32 cols): the hidden chunk is the A operand of the second contraction;
+//   * GEMM2(c): D2 (TMEM, 128 cols) += H[tmem] . W2c^T            (4 x tcgen05.mma 128x128x8, A from TMEM)
+//   * final epilogue (8 warps): tcgen05.ld D2 -> +b2 + skip(h1 fp32) -> BN2 -> h_out (+ TF32 copy),
+//     through a swizzled staging tile so that global memory only sees full 128-byte lines.
+// The MMA warp issues GEMM1(c+1) before GEMM2(c) so the tensor core works while epilogue-1 runs.
+// TMEM columns: D2 [0,128) | D1[g] [128+32g,+32) | H[g] [192+32g,+32) | A [256,384)  (512 allocated).
 // ================================================================================================
 constexpr int FF_HC = 32;                              // hidden units per chunk
 constexpr int FF_CHUNKS = HID_ / FF_HC;                // 16
-constexpr int FF_WSTAGES = 5;
+constexpr int FF_WSTAGES = 7;
 constexpr int FF_WSTAGE_BYTES = 16384;                 // W1c: 4 boxes [32 x 32]; W2c: 1 box [128 x 32]
 constexpr int FF_A_BYTES = BM * D_ * 4;                // 64 KB: 4 boxes [128 x 32]
-constexpr int FF_H_BYTES = BM * FF_HC * 4;             // 16 KB per buffer
 constexpr int FF_SVEC = 3 * D_ + HID_;                 // b2 | bn_scale | bn_shift | b1
-constexpr int FF_THREADS = 11 * 32;                    // warp0 W-TMA, warp1 MMA, warps 2..9 epilogue, warp10 A-TMA
-constexpr int FF_NBARS = 2 + 2 * FF_WSTAGES + 8 + 2;
-constexpr size_t FF_SMEM = 1024 + FF_A_BYTES + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES + 2 * FF_H_BYTES +
-                           EPI_WARPS * STG_TILE_BYTES + FF_SVEC * 4 + FF_NBARS * 8 + 16;
+constexpr int FF_THREADS = 15 * 32;                    // warp0 W-TMA, warp1 MMA, warps 2..9 epilogue, warp10 A-TMA, warps 11..14 A stagers
+constexpr int FF_NBARS = 4 + 2 * FF_WSTAGES + 8 + 2;
+constexpr int FF_TMEM_COLS = 512;
+constexpr size_t FF_SMEM = 1024 + FF_A_BYTES + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES + EPI_WARPS * STG_TILE_BYTES +
+                           FF_SVEC * 4 + FF_NBARS * 8 + 16;
+
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32 (A: lane = row, one fp32 column per k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp writes TMEM lane (lane_base + i)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float *v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(FF_THREADS, 1)
 ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
@@ -497,11 +529,11 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024B-aligned, still .shared
     unsigned char *sA = smem;
     unsigned char *sW = sA + FF_A_BYTES;
-    unsigned char *sH = sW + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES;
-    float *staging = reinterpret_cast<float *>(sH + 2 * FF_H_BYTES);
+    float *staging = reinterpret_cast<float *>(sW + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES);
     float *svec = staging + EPI_WARPS * (STG_TILE_BYTES / 4);
     uint64_t *bars = reinterpret_cast<uint64_t *>(svec + FF_SVEC);
-    uint64_t *a_full = bars, *a_empty = bars + 1, *w_full = bars + 2, *w_empty = w_full + FF_WSTAGES;
+    uint64_t *a_full = bars, *a_empty = bars + 1, *at_full = bars + 2, *at_empty = bars + 3;
+    uint64_t *w_full = bars + 4, *w_empty = w_full + FF_WSTAGES;
     uint64_t *d1_full = w_empty + FF_WSTAGES, *d1_empty = d1_full + 2, *h_full = d1_empty + 2, *h_empty = h_full + 2;
     uint64_t *d2_full = h_empty + 2, *d2_empty = d2_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 1);
@@ -513,7 +545,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int c = threadIdx.x; c < HID_; c += FF_THREADS) svec[3 * D_ + c] = b1[c];
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
-        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        mbar_init(a_full, 1); mbar_init(a_empty, 4); mbar_init(at_full, 4); mbar_init(at_empty, 1);
         for (int s = 0; s < FF_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int g = 0; g < 2; ++g) {
             mbar_init(&d1_full[g], 1); mbar_init(&d1_empty[g], 4);
@@ -522,22 +554,47 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_init(d2_full, 1); mbar_init(d2_empty, EPI_WARPS);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 1) tmem_alloc(tmem_slot, FF_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tm_d2 = tmem_base, tm_d1 = tmem_base + BN;      // D2: cols [0,128); D1[g]: [128+32g, +32)
+    const uint32_t tm_d2 = tmem_base, tm_d1 = tmem_base + 128, tm_h = tmem_base + 192, tm_a = tmem_base + 256;
 
     if (warp == 10) {
-        // ------------------------------------------------------------------ A-tile producer
+        // ------------------------------------------------------------------ A-tile TMA producer
         if (lane == 0) {
             uint32_t it = 0;
             for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
-                mbar_wait(a_empty, (it & 1) ^ 1);
+                mbar_wait(a_empty, (it & 1) ^ 1);             // stagers have copied the previous tile out of smem
                 mbar_expect_tx(a_full, FF_A_BYTES);
                 for (int kb = 0; kb < D_ / BK; ++kb) tma_load_2d(&tmA, a_full, sA + kb * (BM * BK * 4), kb * BK, (int)w * BM);
             }
+        }
+    } else if (warp >= 11) {
+        // ------------------------------------------------------------------ A stagers: smem (128B-swizzled rows) -> TMEM
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        uint32_t it = 0;
+        for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
+            mbar_wait(a_full, it & 1);
+            mbar_wait(at_empty, (it & 1) ^ 1);                // GEMM1 of the previous tile has finished reading A[tmem]
+            tc_fence_after();
+#pragma unroll 1
+            for (int kb = 0; kb < D_ / BK; ++kb) {
+                float v[32];
+                const unsigned char *row = sA + kb * (BM * BK * 4) + r * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 x = *reinterpret_cast<const float4 *>(row + ((j ^ (r & 7)) << 4));
+                    v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+                }
+                tmem_st_32x32(tm_a + ((uint32_t)(q * 32) << 16) + kb * BK, v);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(a_empty); mbar_arrive(at_full); }
         }
     } else if (warp == 0) {
         // ------------------------------------------------------------------ weight producer (ring order == MMA order)
@@ -569,17 +626,15 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         constexpr uint32_t idesc1 = make_idesc_tf32(BM, FF_HC), idesc2 = make_idesc_tf32(BM, BN);
         uint32_t stage = 0, phase = 0, it = 0;
         uint32_t n_d1[2] = {0, 0}, n_h[2] = {0, 0};
-        const uint32_t aA = smem_u32(sA);
         auto gemm2 = [&](int c) {
             const int g = c & 1;
-            mbar_wait(&h_full[g], n_h[g] & 1); ++n_h[g];          // epilogue-1 has written Hc[g]
+            mbar_wait(&h_full[g], n_h[g] & 1); ++n_h[g];          // epilogue-1 has written H[g] (TMEM)
             mbar_wait(&w_full[stage], phase);
             tc_fence_after();
-            const uint64_t da = make_sw128_kmajor_desc(smem_u32(sH + g * FF_H_BYTES));
             const uint64_t db = make_sw128_kmajor_desc(smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES));
             if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < FF_HC / 8; ++k) umma_tf32(tm_d2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (c | k) != 0);
+                for (int k = 0; k < FF_HC / 8; ++k) umma_tf32_ts(tm_d2, tm_h + g * FF_HC + 8 * k, db + (uint64_t)(2 * k), idesc2, (c | k) != 0);
                 umma_commit(&w_empty[stage]);
                 umma_commit(&h_empty[g]);
             }
@@ -587,7 +642,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
         };
         for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
-            mbar_wait(a_full, it & 1);
+            mbar_wait(at_full, it & 1);                       // A tile is in TMEM
             for (int c = 0; c < FF_CHUNKS; ++c) {
                 const int g = c & 1;
                 mbar_wait(&d1_empty[g], (n_d1[g] & 1) ^ 1); ++n_d1[g];   // epilogue-1 drained D1[g]
@@ -597,15 +652,14 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (elect_one()) {
 #pragma unroll
                     for (int kb = 0; kb < D_ / BK; ++kb) {
-                        const uint64_t da = make_sw128_kmajor_desc(aA + kb * (BM * BK * 4));
                         const uint64_t db = make_sw128_kmajor_desc(sw + kb * (FF_HC * BK * 4));
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k)
-                            umma_tf32(tm_d1 + g * FF_HC, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb | k) != 0);
+                            umma_tf32_ts(tm_d1 + g * FF_HC, tm_a + kb * BK + 8 * k, db + (uint64_t)(2 * k), idesc1, (kb | k) != 0);
                     }
                     umma_commit(&w_empty[stage]);
                     umma_commit(&d1_full[g]);
-                    if (c == FF_CHUNKS - 1) umma_commit(a_empty);     // last reader of the A tile
+                    if (c == FF_CHUNKS - 1) umma_commit(at_empty);    // last reader of A[tmem]
                 }
                 __syncwarp();
                 if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
@@ -620,32 +674,30 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ------------------------------------------------------------------ epilogue warps
         const int q = warp & 3;                               // TMEM lane quarter
         const int g = (warp - 2) >> 2;                        // chunk parity handled by this warp group
-        const int r_in_tile = q * 32 + lane;
-        uint32_t n_e1 = 0, it = 0;
-        unsigned char *hrow = sH + g * FF_H_BYTES + r_in_tile * 128;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         float *stg = staging + (warp - 2) * (STG_TILE_BYTES / 4);
+        uint32_t n_e1 = 0, it = 0;
         for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
             for (int c = g; c < FF_CHUNKS; c += 2, ++n_e1) {
                 mbar_wait(&d1_full[g], n_e1 & 1);
                 tc_fence_after();
                 float v[32];
-                tmem_ld_32x32(tm_d1 + ((uint32_t)(q * 32) << 16) + g * FF_HC, v);
+                tmem_ld_32x32(tm_d1 + lane_sel + g * FF_HC, v);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d1_empty[g]);     // D1[g] is in registers now
-                mbar_wait(&h_empty[g], (n_e1 & 1) ^ 1);       // GEMM2 of chunk c-2 has finished reading Hc[g]
                 const float *bb = svec + 3 * D_ + c * FF_HC;
-                float4 bias[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) bias[j] = *reinterpret_cast<const float4 *>(bb + 4 * j);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {                 // 16-byte piece j of this row, 128B swizzle
-                    float4 r;
-                    r.x = tf32_rna(fmaxf(v[4 * j] + bias[j].x, 0.f)); r.y = tf32_rna(fmaxf(v[4 * j + 1] + bias[j].y, 0.f));
-                    r.z = tf32_rna(fmaxf(v[4 * j + 2] + bias[j].z, 0.f)); r.w = tf32_rna(fmaxf(v[4 * j + 3] + bias[j].w, 0.f));
-                    *reinterpret_cast<float4 *>(hrow + ((j ^ (r_in_tile & 7)) << 4)) = r;
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = *reinterpret_cast<const float4 *>(bb + 4 * j);
+                    v[4 * j] = tf32_rna(fmaxf(v[4 * j] + b.x, 0.f)); v[4 * j + 1] = tf32_rna(fmaxf(v[4 * j + 1] + b.y, 0.f));
+                    v[4 * j + 2] = tf32_rna(fmaxf(v[4 * j + 2] + b.z, 0.f)); v[4 * j + 3] = tf32_rna(fmaxf(v[4 * j + 3] + b.w, 0.f));
                 }
-                fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core
+                mbar_wait(&h_empty[g], (n_e1 & 1) ^ 1);       // GEMM2 of chunk c-2 has finished reading H[g]
+                tc_fence_after();
+                tmem_st_32x32(tm_h + lane_sel + g * FF_HC, v);
+                tmem_st_wait();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&h_full[g]);
             }
@@ -656,7 +708,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int c2 = 0; c2 < 2; ++c2) {
                 const int col = g * 64 + c2 * 32;
                 float v[32];
-                tmem_ld_32x32(tm_d2 + ((uint32_t)(q * 32) << 16) + col, v);
+                tmem_ld_32x32(tm_d2 + lane_sel + col, v);
                 epilogue_tile32<EPI_FF2>(p, svec, stg, w * BM + q * 32, col, v, lane);
             }
             tc_fence_before();
@@ -668,7 +720,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(tmem_base, FF_TMEM_COLS);
     }
 }
 
