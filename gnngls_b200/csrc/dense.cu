@@ -469,31 +469,33 @@ int launch_tc_gemm(const float *A, const float *W, const EpiParams &p, cudaStrea
 //
 // One persistent CTA per 128-row tile; the 128x512 hidden activation never leaves the SM and BOTH
 // left-hand operands live in tensor memory, so shared memory only carries the streamed weights:
-//   * A tile (TF32 copy of h1): TMA -> smem (64 KB) -> four "stager" warps copy it into TMEM
-//     (tcgen05.st, lane = row, column = k); the smem buffer is released at once, so the next tile's
-//     TMA overlaps the whole tile.  Re-reading A from smem for each of the 16 hidden chunks was the
-//     shared-memory-port bottleneck of the first version (tools/umma_bench.cu: 40 cycles per N=32 MMA).
-//   * W1 / W2 stream through a TMA ring in chunks of 32 hidden units (16 KB per stage);
-//   * GEMM1(c): D1[c&1] (TMEM, 32 cols) = A[tmem] . W1c^T        (16 x tcgen05.mma 128x32x8, A from TMEM)
-//   * epilogue-1 (4 warps per chunk parity): tcgen05.ld -> +b1, ReLU, cvt.rna.tf32 -> tcgen05.st into
-//     H[c&1] (TMEM, 32 cols): the hidden chunk is the A operand of the second contraction;
-//   * GEMM2(c): D2 (TMEM, 128 cols) += H[tmem] . W2c^T            (4 x tcgen05.mma 128x128x8, A from TMEM)
-//   * final epilogue (8 warps): tcgen05.ld D2 -> +b2 + skip(h1 fp32) -> BN2 -> h_out (+ TF32 copy),
-//     through a swizzled staging tile so that global memory only sees full 128-byte lines.
-// The MMA warp issues GEMM1(c+1) before GEMM2(c) so the tensor core works while epilogue-1 runs.
-// TMEM columns: D2 [0,128) | D1[g] [128+32g,+32) | H[g] [192+32g,+32) | A [256,384)  (512 allocated).
+//   * A tile (TF32 copy of h1): TMA -> smem (64 KB) -> four warps copy it into TMEM (tcgen05.st,
+//     lane = row, column = k); the smem buffer is released at once, so the next tile's TMA overlaps
+//     the whole tile.  (Re-reading A from smem for every hidden chunk made the first version
+//     shared-memory-port bound: tools/umma_bench.cu measures 40 cycles per N=32 smem-A MMA.)
+//   * W1 / W2 stream through a 7-stage TMA ring of 16 KB half-chunks (64 hidden units per chunk);
+//   * GEMM1(c): DH[c&1] (TMEM, 64 cols) = A[tmem] . W1c^T         (16 x tcgen05.mma 128x64x8)
+//   * epilogue-1 (4 warps per chunk parity): tcgen05.ld -> +b1, ReLU, cvt.rna.tf32 -> tcgen05.st back
+//     IN PLACE: the hidden chunk becomes the TMEM A operand of the second contraction;
+//   * GEMM2(c): D2[tile&1] (TMEM, 128 cols) += H[tmem] . W2c^T    (8 x tcgen05.mma 128x128x8)
+//   * final epilogue (the four A-staging warps, one tile behind, D2 double-buffered): tcgen05.ld ->
+//     +b2 + skip(h1 fp32) -> BN2 -> h_out (+ TF32 copy) through a swizzled staging tile so that
+//     global memory only sees full 128-byte lines.
+// MMAs of one thread execute in order, so DH[g] needs no "empty" barriers: GEMM1(c+2) is issued after
+// GEMM2(c).  The MMA warp issues GEMM1(c+1) before GEMM2(c) so the tensor core works during epilogue-1.
+// TMEM columns: D2[0] [0,128) | D2[1] [128,256) | DH[g] [256+64g,+64) | A [384,512).
 // ================================================================================================
-constexpr int FF_HC = 32;                              // hidden units per chunk
-constexpr int FF_CHUNKS = HID_ / FF_HC;                // 16
+constexpr int FF_HC = 64;                              // hidden units per chunk
+constexpr int FF_CHUNKS = HID_ / FF_HC;                // 8
 constexpr int FF_WSTAGES = 7;
-constexpr int FF_WSTAGE_BYTES = 16384;                 // W1c: 4 boxes [32 x 32]; W2c: 1 box [128 x 32]
+constexpr int FF_WSTAGE_BYTES = 16384;                 // half of W1c: 2 boxes [64 x 32]; half of W2c: 1 box [128 x 32]
 constexpr int FF_A_BYTES = BM * D_ * 4;                // 64 KB: 4 boxes [128 x 32]
 constexpr int FF_SVEC = 3 * D_ + HID_;                 // b2 | bn_scale | bn_shift | b1
-constexpr int FF_THREADS = 15 * 32;                    // warp0 W-TMA, warp1 MMA, warps 2..9 epilogue, warp10 A-TMA, warps 11..14 A stagers
-constexpr int FF_NBARS = 4 + 2 * FF_WSTAGES + 8 + 2;
+constexpr int FF_THREADS = 15 * 32;                    // warp0 W-TMA, warp1 MMA, warps 2..9 epilogue-1, warp10 A-TMA, warps 11..14 A staging + final epilogue
+constexpr int FF_NBARS = 4 + 2 * FF_WSTAGES + 8;
 constexpr int FF_TMEM_COLS = 512;
-constexpr size_t FF_SMEM = 1024 + FF_A_BYTES + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES + EPI_WARPS * STG_TILE_BYTES +
-                           FF_SVEC * 4 + FF_NBARS * 8 + 16;
+constexpr size_t FF_SMEM = 1024 + FF_A_BYTES + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES + 4 * STG_TILE_BYTES + FF_SVEC * 4 +
+                           FF_NBARS * 8 + 16;
 
 // D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32 (A: lane = row, one fp32 column per k)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -530,13 +532,12 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     unsigned char *sA = smem;
     unsigned char *sW = sA + FF_A_BYTES;
     float *staging = reinterpret_cast<float *>(sW + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES);
-    float *svec = staging + EPI_WARPS * (STG_TILE_BYTES / 4);
+    float *svec = staging + 4 * (STG_TILE_BYTES / 4);
     uint64_t *bars = reinterpret_cast<uint64_t *>(svec + FF_SVEC);
     uint64_t *a_full = bars, *a_empty = bars + 1, *at_full = bars + 2, *at_empty = bars + 3;
     uint64_t *w_full = bars + 4, *w_empty = w_full + FF_WSTAGES;
-    uint64_t *d1_full = w_empty + FF_WSTAGES, *d1_empty = d1_full + 2, *h_full = d1_empty + 2, *h_empty = h_full + 2;
-    uint64_t *d2_full = h_empty + 2, *d2_empty = d2_full + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 1);
+    uint64_t *d1_full = w_empty + FF_WSTAGES, *h_full = d1_full + 2, *d2_full = h_full + 2, *d2_empty = d2_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m_tiles = (p.M + BM - 1) / BM;
@@ -548,10 +549,9 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_init(a_full, 1); mbar_init(a_empty, 4); mbar_init(at_full, 4); mbar_init(at_empty, 1);
         for (int s = 0; s < FF_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int g = 0; g < 2; ++g) {
-            mbar_init(&d1_full[g], 1); mbar_init(&d1_empty[g], 4);
-            mbar_init(&h_full[g], 4); mbar_init(&h_empty[g], 1);
+            mbar_init(&d1_full[g], 1); mbar_init(&h_full[g], 4);
+            mbar_init(&d2_full[g], 1); mbar_init(&d2_empty[g], 4);
         }
-        mbar_init(d2_full, 1); mbar_init(d2_empty, EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, FF_TMEM_COLS);
@@ -559,23 +559,40 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tm_d2 = tmem_base, tm_d1 = tmem_base + 128, tm_h = tmem_base + 192, tm_a = tmem_base + 256;
+    const uint32_t tm_d2 = tmem_base, tm_dh = tmem_base + 256, tm_a = tmem_base + 384;
 
     if (warp == 10) {
         // ------------------------------------------------------------------ A-tile TMA producer
         if (lane == 0) {
             uint32_t it = 0;
             for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
-                mbar_wait(a_empty, (it & 1) ^ 1);             // stagers have copied the previous tile out of smem
+                mbar_wait(a_empty, (it & 1) ^ 1);             // the previous tile has been copied out of smem
                 mbar_expect_tx(a_full, FF_A_BYTES);
                 for (int kb = 0; kb < D_ / BK; ++kb) tma_load_2d(&tmA, a_full, sA + kb * (BM * BK * 4), kb * BK, (int)w * BM);
             }
         }
     } else if (warp >= 11) {
-        // ------------------------------------------------------------------ A stagers: smem (128B-swizzled rows) -> TMEM
+        // ------------------------------------------------------------------ A staging (smem -> TMEM) + final epilogue, one tile behind
         const int q = warp & 3;
         const int r = q * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        float *stg = staging + (warp - 11) * (STG_TILE_BYTES / 4);
+        auto final_epilogue = [&](int64_t w, uint32_t t) {    // tile index w, local tile counter t
+            const uint32_t d = t & 1;
+            mbar_wait(&d2_full[d], (t >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c2 = 0; c2 < BN / 32; ++c2) {
+                float v[32];
+                tmem_ld_32x32(tm_d2 + lane_sel + d * BN + c2 * 32, v);
+                epilogue_tile32<EPI_FF2>(p, svec, stg, w * BM + q * 32, c2 * 32, v, lane);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d2_empty[d]);
+        };
         uint32_t it = 0;
+        int64_t w_prev = -1;
         for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
             mbar_wait(a_full, it & 1);
             mbar_wait(at_empty, (it & 1) ^ 1);                // GEMM1 of the previous tile has finished reading A[tmem]
@@ -589,131 +606,129 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     const float4 x = *reinterpret_cast<const float4 *>(row + ((j ^ (r & 7)) << 4));
                     v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
                 }
-                tmem_st_32x32(tm_a + ((uint32_t)(q * 32) << 16) + kb * BK, v);
+                tmem_st_32x32(tm_a + lane_sel + kb * BK, v);
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(a_empty); mbar_arrive(at_full); }
+            if (w_prev >= 0) final_epilogue(w_prev, it - 1);
+            w_prev = w;
         }
+        if (w_prev >= 0) final_epilogue(w_prev, it - 1);
     } else if (warp == 0) {
         // ------------------------------------------------------------------ weight producer (ring order == MMA order)
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            auto load_w1 = [&](int c) {
+            auto load_w1 = [&](int c, int half) {             // hidden units [64c, 64c+64), K range [64*half, +64)
                 mbar_wait(&w_empty[stage], phase ^ 1);
                 unsigned char *dst = sW + (size_t)stage * FF_WSTAGE_BYTES;
                 mbar_expect_tx(&w_full[stage], FF_WSTAGE_BYTES);
-                for (int kb = 0; kb < D_ / BK; ++kb) tma_load_2d(&tmW1, &w_full[stage], dst + kb * (FF_HC * BK * 4), kb * BK, c * FF_HC);
+                for (int kk = 0; kk < 2; ++kk) tma_load_2d(&tmW1, &w_full[stage], dst + kk * (FF_HC * BK * 4), (2 * half + kk) * BK, c * FF_HC);
                 if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
             };
-            auto load_w2 = [&](int c) {
+            auto load_w2 = [&](int c, int half) {             // all 128 outputs, hidden units [64c + 32*half, +32)
                 mbar_wait(&w_empty[stage], phase ^ 1);
                 mbar_expect_tx(&w_full[stage], FF_WSTAGE_BYTES);
-                tma_load_2d(&tmW2, &w_full[stage], sW + (size_t)stage * FF_WSTAGE_BYTES, c * FF_HC, 0);
+                tma_load_2d(&tmW2, &w_full[stage], sW + (size_t)stage * FF_WSTAGE_BYTES, c * FF_HC + half * BK, 0);
                 if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
             };
             for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x) {
                 for (int c = 0; c < FF_CHUNKS; ++c) {
-                    load_w1(c);
-                    if (c >= 1) load_w2(c - 1);
+                    load_w1(c, 0); load_w1(c, 1);
+                    if (c >= 1) { load_w2(c - 1, 0); load_w2(c - 1, 1); }
                 }
-                load_w2(FF_CHUNKS - 1);
+                load_w2(FF_CHUNKS - 1, 0); load_w2(FF_CHUNKS - 1, 1);
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (warp-uniform control flow)
         constexpr uint32_t idesc1 = make_idesc_tf32(BM, FF_HC), idesc2 = make_idesc_tf32(BM, BN);
         uint32_t stage = 0, phase = 0, it = 0;
-        uint32_t n_d1[2] = {0, 0}, n_h[2] = {0, 0};
-        auto gemm2 = [&](int c) {
-            const int g = c & 1;
-            mbar_wait(&h_full[g], n_h[g] & 1); ++n_h[g];          // epilogue-1 has written H[g] (TMEM)
-            mbar_wait(&w_full[stage], phase);
-            tc_fence_after();
-            const uint64_t db = make_sw128_kmajor_desc(smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES));
-            if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < FF_HC / 8; ++k) umma_tf32_ts(tm_d2, tm_h + g * FF_HC + 8 * k, db + (uint64_t)(2 * k), idesc2, (c | k) != 0);
-                umma_commit(&w_empty[stage]);
-                umma_commit(&h_empty[g]);
-            }
-            __syncwarp();
-            if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
-        };
+        uint32_t n_h[2] = {0, 0};
         for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
+            const uint32_t d = it & 1;
+            const uint32_t tm_acc = tm_d2 + d * BN;
+            auto gemm2 = [&](int c) {
+                const int g = c & 1;
+                mbar_wait(&h_full[g], n_h[g] & 1); ++n_h[g];  // epilogue-1 has rewritten DH[g] with the hidden chunk
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait(&w_full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t db = make_sw128_kmajor_desc(smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES));
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k)
+                            umma_tf32_ts(tm_acc, tm_dh + g * FF_HC + half * BK + 8 * k, db + (uint64_t)(2 * k), idesc2, (c | half | k) != 0);
+                        umma_commit(&w_empty[stage]);
+                    }
+                    __syncwarp();
+                    if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                }
+            };
             mbar_wait(at_full, it & 1);                       // A tile is in TMEM
             for (int c = 0; c < FF_CHUNKS; ++c) {
                 const int g = c & 1;
-                mbar_wait(&d1_empty[g], (n_d1[g] & 1) ^ 1); ++n_d1[g];   // epilogue-1 drained D1[g]
-                mbar_wait(&w_full[stage], phase);
-                tc_fence_after();
-                const uint32_t sw = smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES);
-                if (elect_one()) {
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait(&w_full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sw = smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kb = 0; kb < D_ / BK; ++kb) {
-                        const uint64_t db = make_sw128_kmajor_desc(sw + kb * (FF_HC * BK * 4));
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint64_t db = make_sw128_kmajor_desc(sw + kk * (FF_HC * BK * 4));
 #pragma unroll
-                        for (int k = 0; k < BK / 8; ++k)
-                            umma_tf32_ts(tm_d1 + g * FF_HC, tm_a + kb * BK + 8 * k, db + (uint64_t)(2 * k), idesc1, (kb | k) != 0);
+                            for (int k = 0; k < BK / 8; ++k)
+                                umma_tf32_ts(tm_dh + g * FF_HC, tm_a + (2 * half + kk) * BK + 8 * k, db + (uint64_t)(2 * k), idesc1,
+                                             (half | kk | k) != 0);
+                        }
+                        umma_commit(&w_empty[stage]);
+                        if (half == 1) {
+                            umma_commit(&d1_full[g]);
+                            if (c == FF_CHUNKS - 1) umma_commit(at_empty);   // last reader of A[tmem]
+                        }
                     }
-                    umma_commit(&w_empty[stage]);
-                    umma_commit(&d1_full[g]);
-                    if (c == FF_CHUNKS - 1) umma_commit(at_empty);    // last reader of A[tmem]
+                    __syncwarp();
+                    if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
-                if (c == 1) { mbar_wait(d2_empty, (it & 1) ^ 1); tc_fence_after(); }   // before GEMM2(0) overwrites D2
+                if (c == 1) { mbar_wait(&d2_empty[d], ((it >> 1) & 1) ^ 1); tc_fence_after(); }   // final epilogue two tiles back drained D2[d]
                 if (c >= 1) gemm2(c - 1);
             }
             gemm2(FF_CHUNKS - 1);
-            if (elect_one()) umma_commit(d2_full);
+            if (elect_one()) umma_commit(&d2_full[d]);
             __syncwarp();
         }
     } else {
-        // ------------------------------------------------------------------ epilogue warps
+        // ------------------------------------------------------------------ epilogue-1 warps
         const int q = warp & 3;                               // TMEM lane quarter
         const int g = (warp - 2) >> 2;                        // chunk parity handled by this warp group
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        float *stg = staging + (warp - 2) * (STG_TILE_BYTES / 4);
-        uint32_t n_e1 = 0, it = 0;
-        for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
+        uint32_t n_e1 = 0;
+        for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x) {
             for (int c = g; c < FF_CHUNKS; c += 2, ++n_e1) {
                 mbar_wait(&d1_full[g], n_e1 & 1);
                 tc_fence_after();
-                float v[32];
-                tmem_ld_32x32(tm_d1 + lane_sel + g * FF_HC, v);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&d1_empty[g]);     // D1[g] is in registers now
-                const float *bb = svec + 3 * D_ + c * FF_HC;
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    float v[32];
+                    const uint32_t ta = tm_dh + lane_sel + g * FF_HC + hf * 32;
+                    tmem_ld_32x32(ta, v);
+                    const float *bb = svec + 3 * D_ + c * FF_HC + hf * 32;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b = *reinterpret_cast<const float4 *>(bb + 4 * j);
-                    v[4 * j] = tf32_rna(fmaxf(v[4 * j] + b.x, 0.f)); v[4 * j + 1] = tf32_rna(fmaxf(v[4 * j + 1] + b.y, 0.f));
-                    v[4 * j + 2] = tf32_rna(fmaxf(v[4 * j + 2] + b.z, 0.f)); v[4 * j + 3] = tf32_rna(fmaxf(v[4 * j + 3] + b.w, 0.f));
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = *reinterpret_cast<const float4 *>(bb + 4 * j);
+                        v[4 * j] = tf32_rna(fmaxf(v[4 * j] + b.x, 0.f)); v[4 * j + 1] = tf32_rna(fmaxf(v[4 * j + 1] + b.y, 0.f));
+                        v[4 * j + 2] = tf32_rna(fmaxf(v[4 * j + 2] + b.z, 0.f)); v[4 * j + 3] = tf32_rna(fmaxf(v[4 * j + 3] + b.w, 0.f));
+                    }
+                    tmem_st_32x32(ta, v);                     // in place: D1 -> H
                 }
-                mbar_wait(&h_empty[g], (n_e1 & 1) ^ 1);       // GEMM2 of chunk c-2 has finished reading H[g]
-                tc_fence_after();
-                tmem_st_32x32(tm_h + lane_sel + g * FF_HC, v);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&h_full[g]);
             }
-            // final epilogue: this group owns 64 of the 128 output columns
-            mbar_wait(d2_full, it & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c2 = 0; c2 < 2; ++c2) {
-                const int col = g * 64 + c2 * 32;
-                float v[32];
-                tmem_ld_32x32(tm_d2 + lane_sel + col, v);
-                epilogue_tile32<EPI_FF2>(p, svec, stg, w * BM + q * 32, col, v, lane);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(d2_empty);
         }
     }
     tc_fence_before();
@@ -727,7 +742,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 int launch_ff_fused(const float *a_op, const float *W1, const float *b1, const float *W2, const EpiParams &p, cudaStream_t st) {
     CUtensorMap tmA, tmW1, tmW2;
     if (int rc = make_map(&tmA, a_op, (uint64_t)p.M, D_, BM)) return rc;
-    if (int rc = make_map(&tmW1, W1, HID_, D_, FF_HC)) return rc;
+    if (int rc = make_map(&tmW1, W1, HID_, D_, FF_HC)) return rc;      // box [64 hidden x 32 k]
     if (int rc = make_map(&tmW2, W2, D_, HID_, BM)) return rc;
     GNNGLS_CUDA_OK(cudaFuncSetAttribute(ff_fused_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
     const int64_t tiles = (p.M + BM - 1) / BM;
