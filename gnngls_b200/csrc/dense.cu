@@ -18,6 +18,7 @@
 // are K=in_dim / N=out_dim degenerate and run as fused elementwise / dot-product kernels.
 #include <cuda.h>
 #include <cstdint>
+#include <cstdlib>
 #include "common.h"
 
 namespace {
@@ -25,6 +26,7 @@ namespace {
 constexpr int D_ = GNNGLS_EMBED_DIM;     // 128
 constexpr int H_ = GNNGLS_HEADS;         // 8
 constexpr int HID_ = GNNGLS_HIDDEN_DIM;  // 512
+constexpr float kLog2e = 1.4426950408889634f;
 
 enum { EPI_FC = 0, EPI_FF1 = 1, EPI_FF2 = 2 };
 
@@ -37,7 +39,7 @@ struct EpiParams {
     const float *v1;     // FC: attn_r[128]; FF2: bn_scale[128]
     const float *v2;     // FF2: bn_shift[128]
     const float *skip;   // FF2: h1 [M,128] (fp32, unrounded)
-    int round_tf32;      // FF1: store the hidden activations rounded to TF32 (they only feed the next GEMM)
+    int round_tf32;      // FC: store ft rounded to TF32; FF1 (debug path): same for the hidden activations
 };
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -63,10 +65,10 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams &p, int64_t row, i
         sl += __shfl_xor_sync(0xffffffffu, sl, 2);
         sr += __shfl_xor_sync(0xffffffffu, sr, 2);
         if (valid) {
-            *reinterpret_cast<float4 *>(p.out + row * D_ + col) = acc;
+            *reinterpret_cast<float4 *>(p.out + row * D_ + col) = p.round_tf32 ? tf32_rna4(acc) : acc;
             if ((col & 15) == 0) {   // first quad of a head: 16 columns per head
-                p.el[row * H_ + (col >> 4)] = sl;
-                p.er[row * H_ + (col >> 4)] = sr;
+                p.el[row * H_ + (col >> 4)] = sl * kLog2e;
+                p.er[row * H_ + (col >> 4)] = sr * kLog2e;
             }
         }
     } else if (EPI == EPI_FF1) {
@@ -137,11 +139,13 @@ __device__ __forceinline__ void epilogue_tile32(const EpiParams &p, const float 
             const float4 ar = *reinterpret_cast<const float4 *>(sv + D_ + col + 4 * j);
             sl[j >> 2] += v[4 * j] * al.x + v[4 * j + 1] * al.y + v[4 * j + 2] * al.z + v[4 * j + 3] * al.w;
             sr[j >> 2] += v[4 * j] * ar.x + v[4 * j + 1] * ar.y + v[4 * j + 2] * ar.z + v[4 * j + 3] * ar.w;
-            *stg_slot(stg, lane, j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (p.round_tf32) o = tf32_rna4(o);             // ft only feeds the aggregate's tensor-core B operand
+            *stg_slot(stg, lane, j) = o;
         }
         if (row < p.M) {
-            *reinterpret_cast<float2 *>(p.el + row * H_ + (col >> 4)) = make_float2(sl[0], sl[1]);
-            *reinterpret_cast<float2 *>(p.er + row * H_ + (col >> 4)) = make_float2(sr[0], sr[1]);
+            *reinterpret_cast<float2 *>(p.el + row * H_ + (col >> 4)) = make_float2(sl[0] * kLog2e, sl[1] * kLog2e);
+            *reinterpret_cast<float2 *>(p.er + row * H_ + (col >> 4)) = make_float2(sr[0] * kLog2e, sr[1] * kLog2e);
         }
         __syncwarp();
         stg_store_tile(stg, p.out, nullptr, row0, col, D_, p.M, lane);
@@ -226,6 +230,22 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, and each
+// destination CTA's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -250,6 +270,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// same, arriving on the barrier at this offset in every CTA of `mask` (operands were multicast to all of them)
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives TMEM lane (lane_base + i)
@@ -475,7 +501,7 @@ int launch_tc_gemm(const float *A, const float *W, const EpiParams &p, cudaStrea
 //     shared-memory-port bound: tools/umma_bench.cu measures 40 cycles per N=32 smem-A MMA.)
 //   * W1 / W2 stream through a 7-stage TMA ring of 16 KB half-chunks (64 hidden units per chunk);
 //   * GEMM1(c): DH[c&1] (TMEM, 64 cols) = A[tmem] . W1c^T         (16 x tcgen05.mma 128x64x8)
-//   * epilogue-1 (4 warps per chunk parity): tcgen05.ld -> +b1, ReLU, cvt.rna.tf32 -> tcgen05.st back
+//   * epilogue-1 (8 warps, 32 rows x 32 units each): tcgen05.ld -> +b1, ReLU, cvt.rna.tf32 -> tcgen05.st back
 //     IN PLACE: the hidden chunk becomes the TMEM A operand of the second contraction;
 //   * GEMM2(c): D2[tile&1] (TMEM, 128 cols) += H[tmem] . W2c^T    (8 x tcgen05.mma 128x128x8)
 //   * final epilogue (the four A-staging warps, one tile behind, D2 double-buffered): tcgen05.ld ->
@@ -524,6 +550,7 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float *v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+template <int CL>      // CTAs per cluster sharing (multicasting) the streamed weights: 1, 2 or 4
 __global__ void __launch_bounds__(FF_THREADS, 1)
 ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const EpiParams p, const float *__restrict__ b1) {
@@ -540,16 +567,22 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m_tiles = (p.M + BM - 1) / BM;
+    // Every CTA of a cluster walks the same number of tile groups (the weight ring is shared); a CTA whose
+    // tile index falls past the end runs a dummy tile (TMA zero-fills, stores are masked by row < M).
+    const int64_t m_tiles_real = (p.M + BM - 1) / BM;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    const int64_t tile0 = (int64_t)(blockIdx.x / CL) * CL + crank, tile_step = gridDim.x;
+    const int64_t m_tiles = (m_tiles_real + CL - 1) / CL * CL;       // loops run `w < m_tiles` with w = tile0 + k*tile_step
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
 
     for (int c = threadIdx.x; c < D_; c += FF_THREADS) { svec[c] = p.v0[c]; svec[D_ + c] = p.v1[c]; svec[2 * D_ + c] = p.v2[c]; }
     for (int c = threadIdx.x; c < HID_; c += FF_THREADS) svec[3 * D_ + c] = b1[c];
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
         mbar_init(a_full, 1); mbar_init(a_empty, 4); mbar_init(at_full, 4); mbar_init(at_empty, 1);
-        for (int s = 0; s < FF_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < FF_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
         for (int g = 0; g < 2; ++g) {
-            mbar_init(&d1_full[g], 1); mbar_init(&h_full[g], 4);
+            mbar_init(&d1_full[g], 1); mbar_init(&h_full[g], EPI_WARPS);
             mbar_init(&d2_full[g], 1); mbar_init(&d2_empty[g], 4);
         }
         fence_barrier_init();
@@ -557,6 +590,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 1) tmem_alloc(tmem_slot, FF_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                           // peers' barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tm_d2 = tmem_base, tm_dh = tmem_base + 256, tm_a = tmem_base + 384;
@@ -565,7 +599,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ------------------------------------------------------------------ A-tile TMA producer
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
+            for (int64_t w = tile0; w < m_tiles; w += tile_step, ++it) {
                 mbar_wait(a_empty, (it & 1) ^ 1);             // the previous tile has been copied out of smem
                 mbar_expect_tx(a_full, FF_A_BYTES);
                 for (int kb = 0; kb < D_ / BK; ++kb) tma_load_2d(&tmA, a_full, sA + kb * (BM * BK * 4), kb * BK, (int)w * BM);
@@ -585,7 +619,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int c2 = 0; c2 < BN / 32; ++c2) {
                 float v[32];
                 tmem_ld_32x32(tm_d2 + lane_sel + d * BN + c2 * 32, v);
-                epilogue_tile32<EPI_FF2>(p, svec, stg, w * BM + q * 32, c2 * 32, v, lane);
+                if (!(p.round_tf32 & 2)) epilogue_tile32<EPI_FF2>(p, svec, stg, w * BM + q * 32, c2 * 32, v, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -593,7 +627,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         };
         uint32_t it = 0;
         int64_t w_prev = -1;
-        for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
+        for (int64_t w = tile0; w < m_tiles; w += tile_step, ++it) {
             mbar_wait(a_full, it & 1);
             mbar_wait(at_empty, (it & 1) ^ 1);                // GEMM1 of the previous tile has finished reading A[tmem]
             tc_fence_after();
@@ -620,20 +654,31 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ------------------------------------------------------------------ weight producer (ring order == MMA order)
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            auto load_w1 = [&](int c, int half) {             // hidden units [64c, 64c+64), K range [64*half, +64)
+            // Each stage is 16 KB = CL sub-boxes of [BR rows x 32 k]; this CTA fetches sub-box `crank` and
+            // multicasts it to the whole cluster, so every weight byte crosses L2->SM once per cluster.
+            constexpr int BR = 128 / CL;                      // rows per sub-box (W tensor maps are built with this box height)
+            auto load_w1 = [&](int c, int half) {             // hidden units [64c, 64c+64), K range [64*half, +64): 2 x [64 rows x 32 k]
                 mbar_wait(&w_empty[stage], phase ^ 1);
                 unsigned char *dst = sW + (size_t)stage * FF_WSTAGE_BYTES;
                 mbar_expect_tx(&w_full[stage], FF_WSTAGE_BYTES);
-                for (int kk = 0; kk < 2; ++kk) tma_load_2d(&tmW1, &w_full[stage], dst + kk * (FF_HC * BK * 4), (2 * half + kk) * BK, c * FF_HC);
+                if (CL == 1) {
+                    for (int kk = 0; kk < 2; ++kk) tma_load_2d(&tmW1, &w_full[stage], dst + kk * (FF_HC * BK * 4), (2 * half + kk) * BK, c * FF_HC);
+                } else {
+                    constexpr int per = BR >= 64 ? 1 : 64 / BR;  // sub-boxes per [64 x 32] W1 block
+                    const int kk = (int)crank / per, r0 = ((int)crank % per) * BR;
+                    tma_load_2d_mc(&tmW1, &w_full[stage], dst + kk * (FF_HC * BK * 4) + r0 * 128, (2 * half + kk) * BK, c * FF_HC + r0, kMask);
+                }
                 if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
             };
-            auto load_w2 = [&](int c, int half) {             // all 128 outputs, hidden units [64c + 32*half, +32)
+            auto load_w2 = [&](int c, int half) {             // all 128 outputs, hidden units [64c + 32*half, +32): [128 rows x 32 k]
                 mbar_wait(&w_empty[stage], phase ^ 1);
+                unsigned char *dst = sW + (size_t)stage * FF_WSTAGE_BYTES;
                 mbar_expect_tx(&w_full[stage], FF_WSTAGE_BYTES);
-                tma_load_2d(&tmW2, &w_full[stage], sW + (size_t)stage * FF_WSTAGE_BYTES, c * FF_HC + half * BK, 0);
+                if (CL == 1) tma_load_2d(&tmW2, &w_full[stage], dst, c * FF_HC + half * BK, 0);
+                else tma_load_2d_mc(&tmW2, &w_full[stage], dst + (int)crank * BR * 128, c * FF_HC + half * BK, (int)crank * BR, kMask);
                 if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
             };
-            for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x) {
+            for (int64_t w = tile0; w < m_tiles; w += tile_step) {
                 for (int c = 0; c < FF_CHUNKS; ++c) {
                     load_w1(c, 0); load_w1(c, 1);
                     if (c >= 1) { load_w2(c - 1, 0); load_w2(c - 1, 1); }
@@ -646,12 +691,12 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         constexpr uint32_t idesc1 = make_idesc_tf32(BM, FF_HC), idesc2 = make_idesc_tf32(BM, BN);
         uint32_t stage = 0, phase = 0, it = 0;
         uint32_t n_h[2] = {0, 0};
-        for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x, ++it) {
+        for (int64_t w = tile0; w < m_tiles; w += tile_step, ++it) {
             const uint32_t d = it & 1;
             const uint32_t tm_acc = tm_d2 + d * BN;
             auto gemm2 = [&](int c) {
                 const int g = c & 1;
-                mbar_wait(&h_full[g], n_h[g] & 1); ++n_h[g];  // epilogue-1 has rewritten DH[g] with the hidden chunk
+                if (!(p.round_tf32 & 1)) { mbar_wait(&h_full[g], n_h[g] & 1); } ++n_h[g];  // epilogue-1 has rewritten DH[g] with the hidden chunk
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     mbar_wait(&w_full[stage], phase);
@@ -661,7 +706,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k)
                             umma_tf32_ts(tm_acc, tm_dh + g * FF_HC + half * BK + 8 * k, db + (uint64_t)(2 * k), idesc2, (c | half | k) != 0);
-                        umma_commit(&w_empty[stage]);
+                        if (CL == 1) umma_commit(&w_empty[stage]); else umma_commit_mc(&w_empty[stage], kMask);
                     }
                     __syncwarp();
                     if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
@@ -684,7 +729,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                 umma_tf32_ts(tm_dh + g * FF_HC, tm_a + (2 * half + kk) * BK + 8 * k, db + (uint64_t)(2 * k), idesc1,
                                              (half | kk | k) != 0);
                         }
-                        umma_commit(&w_empty[stage]);
+                        if (CL == 1) umma_commit(&w_empty[stage]); else umma_commit_mc(&w_empty[stage], kMask);
                         if (half == 1) {
                             umma_commit(&d1_full[g]);
                             if (c == FF_CHUNKS - 1) umma_commit(at_empty);   // last reader of A[tmem]
@@ -701,29 +746,28 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             __syncwarp();
         }
     } else {
-        // ------------------------------------------------------------------ epilogue-1 warps
+        // ------------------------------------------------------------------ epilogue-1 warps: all eight work on every
+        // chunk (32 rows x 32 hidden units each), which halves the GEMM1 -> GEMM2 latency of a chunk
         const int q = warp & 3;                               // TMEM lane quarter
-        const int g = (warp - 2) >> 2;                        // chunk parity handled by this warp group
+        const int hf = (warp - 2) >> 2;                       // which 32 of the chunk's 64 hidden units
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        uint32_t n_e1 = 0;
-        for (int64_t w = blockIdx.x; w < m_tiles; w += gridDim.x) {
-            for (int c = g; c < FF_CHUNKS; c += 2, ++n_e1) {
-                mbar_wait(&d1_full[g], n_e1 & 1);
+        uint32_t n_e1[2] = {0, 0};
+        for (int64_t w = tile0; w < m_tiles; w += tile_step) {
+            for (int c = 0; c < FF_CHUNKS; ++c) {
+                const int g = c & 1;
+                mbar_wait(&d1_full[g], n_e1[g] & 1); ++n_e1[g];
                 tc_fence_after();
-#pragma unroll 1
-                for (int hf = 0; hf < 2; ++hf) {
-                    float v[32];
-                    const uint32_t ta = tm_dh + lane_sel + g * FF_HC + hf * 32;
-                    tmem_ld_32x32(ta, v);
-                    const float *bb = svec + 3 * D_ + c * FF_HC + hf * 32;
+                float v[32];
+                const uint32_t ta = tm_dh + lane_sel + g * FF_HC + hf * 32;
+                tmem_ld_32x32(ta, v);
+                const float *bb = svec + 3 * D_ + c * FF_HC + hf * 32;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b = *reinterpret_cast<const float4 *>(bb + 4 * j);
-                        v[4 * j] = tf32_rna(fmaxf(v[4 * j] + b.x, 0.f)); v[4 * j + 1] = tf32_rna(fmaxf(v[4 * j + 1] + b.y, 0.f));
-                        v[4 * j + 2] = tf32_rna(fmaxf(v[4 * j + 2] + b.z, 0.f)); v[4 * j + 3] = tf32_rna(fmaxf(v[4 * j + 3] + b.w, 0.f));
-                    }
-                    tmem_st_32x32(ta, v);                     // in place: D1 -> H
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = *reinterpret_cast<const float4 *>(bb + 4 * j);
+                    v[4 * j] = tf32_rna(fmaxf(v[4 * j] + b.x, 0.f)); v[4 * j + 1] = tf32_rna(fmaxf(v[4 * j + 1] + b.y, 0.f));
+                    v[4 * j + 2] = tf32_rna(fmaxf(v[4 * j + 2] + b.z, 0.f)); v[4 * j + 3] = tf32_rna(fmaxf(v[4 * j + 3] + b.w, 0.f));
                 }
+                tmem_st_32x32(ta, v);                         // in place: D1 -> H
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -733,23 +777,51 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                           // no CTA exits while a peer can still multicast into it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, FF_TMEM_COLS);
     }
 }
 
-int launch_ff_fused(const float *a_op, const float *W1, const float *b1, const float *W2, const EpiParams &p, cudaStream_t st) {
+template <int CL>
+int launch_ff_fused_cl(const float *a_op, const float *W1, const float *b1, const float *W2, const EpiParams &p, cudaStream_t st) {
     CUtensorMap tmA, tmW1, tmW2;
     if (int rc = make_map(&tmA, a_op, (uint64_t)p.M, D_, BM)) return rc;
-    if (int rc = make_map(&tmW1, W1, HID_, D_, FF_HC)) return rc;      // box [64 hidden x 32 k]
-    if (int rc = make_map(&tmW2, W2, D_, HID_, BM)) return rc;
-    GNNGLS_CUDA_OK(cudaFuncSetAttribute(ff_fused_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
+    if (int rc = make_map(&tmW1, W1, HID_, D_, CL == 1 ? FF_HC : 128 / CL)) return rc;     // box [rows x 32 k]
+    if (int rc = make_map(&tmW2, W2, D_, HID_, CL == 1 ? BM : 128 / CL)) return rc;
+    auto kern = ff_fused_tf32_kernel<CL>;
+    GNNGLS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
     const int64_t tiles = (p.M + BM - 1) / BM;
     const int sms = gnngls::device_sm_count();
-    ff_fused_tf32_kernel<<<(int)(tiles < sms ? tiles : sms), FF_THREADS, FF_SMEM, st>>>(tmA, tmW1, tmW2, p, b1);
+    int64_t grid = tiles < sms ? tiles : sms;
+    grid = (grid + CL - 1) / CL * CL;
+    if (grid > sms) grid = sms / CL * CL;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(FF_THREADS);
+    cfg.dynamicSmemBytes = FF_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GNNGLS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmW1, tmW2, p, b1));
     GNNGLS_LAUNCH_OK("ff_fused_tf32_kernel");
     return GNNGLS_OK;
+}
+
+int launch_ff_fused(const float *a_op, const float *W1, const float *b1, const float *W2, const EpiParams &p, cudaStream_t st) {
+    static int cl = -1;                                       // GNNGLS_FF_CLUSTER = 1 | 2 | 4 (default 2)
+    if (cl < 0) {
+        const char *e = getenv("GNNGLS_FF_CLUSTER");
+        cl = e ? atoi(e) : 2;
+        if (cl != 1 && cl != 2 && cl != 4) cl = 2;
+    }
+    if (cl == 1) return launch_ff_fused_cl<1>(a_op, W1, b1, W2, p, st);
+    if (cl == 4) return launch_ff_fused_cl<4>(a_op, W1, b1, W2, p, st);
+    return launch_ff_fused_cl<2>(a_op, W1, b1, W2, p, st);
 }
 
 // ================================================================================================
@@ -875,7 +947,7 @@ extern "C" int gnngls_fc_forward(int impl, const float *h, int64_t M, const floa
     EpiParams p{};
     p.M = M; p.out = ft; p.el = el; p.er = er; p.v0 = attn_l; p.v1 = attn_r;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (impl == GNNGLS_DENSE_TCGEN05) return launch_tc_gemm<D_, D_, EPI_FC>(h, Wfc, p, st);
+    if (impl == GNNGLS_DENSE_TCGEN05) { p.round_tf32 = 1; return launch_tc_gemm<D_, D_, EPI_FC>(h, Wfc, p, st); }
     if (impl == GNNGLS_DENSE_SIMT) return launch_simt_gemm<D_, D_, EPI_FC>(h, Wfc, p, st);
     GNNGLS_REQUIRE(false, GNNGLS_ERR_BAD_ARG, "unknown dense impl %d", impl);
 }
@@ -901,7 +973,12 @@ extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32
     EpiParams p2{};
     p2.M = M; p2.out = h_out; p2.out_tf32 = h_out_tf32; p2.v0 = b2; p2.v1 = bn_scale; p2.v2 = bn_shift; p2.skip = h1;
     const float *a1 = h1_tf32 ? h1_tf32 : h1;                 // GEMM operand; the skip path always reads fp32 h1
-    if (impl == GNNGLS_DENSE_TCGEN05) return launch_ff_fused(a1, W1, b1, W2, p2, st);
+    if (impl == GNNGLS_DENSE_TCGEN05) {
+        static int dbg = -1;                                   // GNNGLS_FF_DEBUG: timing experiments only (wrong results!)
+        if (dbg < 0) { const char *e = getenv("GNNGLS_FF_DEBUG"); dbg = e ? atoi(e) : 0; }
+        p2.round_tf32 = dbg;
+        return launch_ff_fused(a1, W1, b1, W2, p2, st);
+    }
     if (impl == GNNGLS_DENSE_SIMT) {
         if (int rc = launch_simt_gemm<HID_, D_, EPI_FF1>(a1, W1, p1, st)) return rc;
         return launch_simt_gemm<D_, HID_, EPI_FF2>(hid, W2, p2, st);

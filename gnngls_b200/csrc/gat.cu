@@ -19,6 +19,7 @@
 //    epilogue.  Every ft row is read from L2/HBM exactly twice per layer.
 #include <cstdint>
 #include <cmath>
+#include <type_traits>
 #include "common.h"
 
 namespace {
@@ -67,8 +68,8 @@ gat_csr_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, 
         {
             const float4 a = *reinterpret_cast<const float4 *>(er + v * H_);
             const float4 b = *reinterpret_cast<const float4 *>(er + v * H_ + 4);
-            erv[0] = a.x * kLog2e; erv[1] = a.y * kLog2e; erv[2] = a.z * kLog2e; erv[3] = a.w * kLog2e;
-            erv[4] = b.x * kLog2e; erv[5] = b.y * kLog2e; erv[6] = b.z * kLog2e; erv[7] = b.w * kLog2e;
+            erv[0] = a.x; erv[1] = a.y; erv[2] = a.z; erv[3] = a.w;      // el/er arrive pre-multiplied by log2(e)
+            erv[4] = b.x; erv[5] = b.y; erv[6] = b.z; erv[7] = b.w;
         }
         // pass A: per-head maximum of the (log2-scaled) scores over the in-edges
         float mx[H_];
@@ -80,7 +81,7 @@ gat_csr_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, 
             const float4 b = *reinterpret_cast<const float4 *>(el + (int64_t)u * H_ + 4);
             const float l8[H_] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int k = 0; k < H_; ++k) mx[k] = fmaxf(mx[k], lrelu(fmaf(l8[k], kLog2e, erv[k])));
+            for (int k = 0; k < H_; ++k) mx[k] = fmaxf(mx[k], lrelu(l8[k] + erv[k]));
         }
 #pragma unroll
         for (int k = 0; k < H_; ++k)
@@ -99,7 +100,7 @@ gat_csr_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, 
                 const float4 b = *reinterpret_cast<const float4 *>(el + (int64_t)u * H_ + 4);
                 const float l8[H_] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-                for (int k = 0; k < H_; ++k) p[k] = ex2(lrelu(fmaf(l8[k], kLog2e, erv[k])) - mx[k]);
+                for (int k = 0; k < H_; ++k) p[k] = ex2(lrelu(l8[k] + erv[k]) - mx[k]);
             } else {
 #pragma unroll
                 for (int k = 0; k < H_; ++k) p[k] = 0.f;
@@ -174,7 +175,7 @@ __device__ __forceinline__ Top2 top2_merge(Top2 x, Top2 y) {
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline size_t star_smem_bytes(int n) {
     const int KP = round_up(n, 8), MP = round_up(n, 16);
-    return sizeof(float) * ((size_t)KP * FS_LD + (size_t)KP * H_ + (size_t)MP * H_ + 3 * H_);
+    return sizeof(float) * ((size_t)KP * FS_LD + (size_t)KP * H_ + (size_t)MP * H_ + 3 * H_ + (size_t)KP);
 }
 
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -193,18 +194,17 @@ struct StarCtx {
     const float *Fh;      // star features, offset to this warp's head
     const float *ELs, *ERs;
     int ksteps;
-    float *pnum, *pden, *pmax;
+    float *pn, *pd, *pm;  // this star's partial rows: pnum/pden/pmax + ((b*n+i)*n) rows, plus the lane's column offset
 };
 
 // publish one destination row of this warp's head: lane t of the quad holds features {2t,2t+1} and
 // {8+2t,9+2t}.  (.cg stores: the partials are consumed by another SM through L2.)
 __device__ __forceinline__ void publish_row(const StarCtx &c, int j, float2 n0, float2 n1, float den, float mx) {
     if (j >= c.n || j == c.i) return;
-    const int64_t mine = ((int64_t)c.b * c.n + c.i) * c.n + j;
-    float *o = c.pnum + mine * D_ + c.hd * 16 + 2 * c.t;
+    float *o = c.pn + j * D_;
     __stcg(reinterpret_cast<float2 *>(o), n0);
     __stcg(reinterpret_cast<float2 *>(o + 8), n1);
-    if (c.t == 0) { __stcg(c.pden + mine * H_ + c.hd, den); __stcg(c.pmax + mine * H_ + c.hd, mx); }
+    if (c.t == 0) { __stcg(c.pd + j * H_, den); __stcg(c.pm + j * H_, mx); }
 }
 
 // NT m-tiles (16 destinations each) processed together so that el and the B fragments of a k-step
@@ -228,7 +228,9 @@ __device__ __forceinline__ void star_tiles(const StarCtx &c, int mt0) {
         for (int q = 0; q < 4; ++q) { acc0[u][q] = 0.f; acc1[u][q] = 0.f; accs[u][q] = 0.f; }
     }
     const uint32_t one = __float_as_uint(1.0f);
-    for (int ks = 0; ks < c.ksteps; ++ks) {
+    // one k-step (8 star members) for the NT tiles; DIAG = this k-step may contain a destination's own slot
+    auto kstep = [&](int ks, auto diag_tag) {
+        constexpr bool DIAG = decltype(diag_tag)::value;
         const int k_lo = ks * 8 + c.t, k_hi = k_lo + 4;
         const float el_lo = c.ELs[k_lo * H_ + c.hd], el_hi = c.ELs[k_hi * H_ + c.hd];
         const float *r_lo = c.Fh + (size_t)k_lo * FS_LD + c.g, *r_hi = c.Fh + (size_t)k_hi * FS_LD + c.g;
@@ -241,7 +243,7 @@ __device__ __forceinline__ void star_tiles(const StarCtx &c, int mt0) {
             float w1 = ex2(fmaxf(el_lo + c1a[u][1], fmaf(kSlope, el_lo, c2a[u][1])));   // (row hi, col k_lo)
             float w2 = ex2(fmaxf(el_hi + c1a[u][0], fmaf(kSlope, el_hi, c2a[u][0])));   // (row lo, col k_hi)
             float w3 = ex2(fmaxf(el_hi + c1a[u][1], fmaf(kSlope, el_hi, c2a[u][1])));   // (row hi, col k_hi)
-            if ((ks >> 1) == mt0 + u) {                  // tile touches the diagonal: a node is not its own neighbour
+            if (DIAG) {                                  // a node is not its own neighbour
                 const int j_lo = (mt0 + u) * 16 + c.g, j_hi = j_lo + 8;
                 if (k_lo == j_lo) w0 = 0.f;
                 if (k_lo == j_hi) w1 = 0.f;
@@ -253,7 +255,13 @@ __device__ __forceinline__ void star_tiles(const StarCtx &c, int mt0) {
             mma_tf32_16x8x8(acc1[u], a, b10, b11);
             mma_tf32_16x8x8(accs[u], a, one, one);       // row sums of the (truncated) weights
         }
-    }
+    };
+    // destinations of tile mt sit on the diagonal of k-steps 2mt and 2mt+1 only: peel those so the bulk of
+    // the loop carries no masking code
+    const int d0 = min(2 * mt0, c.ksteps), d1 = min(2 * (mt0 + NT), c.ksteps);
+    for (int ks = 0; ks < d0; ++ks) kstep(ks, std::false_type{});
+    for (int ks = d0; ks < d1; ++ks) kstep(ks, std::true_type{});
+    for (int ks = d1; ks < c.ksteps; ++ks) kstep(ks, std::false_type{});
 #pragma unroll
     for (int u = 0; u < NT; ++u) {
         const int j_lo = (mt0 + u) * 16 + c.g;
@@ -267,12 +275,12 @@ gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict_
                    float *__restrict__ pnum, float *__restrict__ pden, float *__restrict__ pmax,
                    int *__restrict__ arrive, const float *__restrict__ h, const float *__restrict__ bias,
                    const float *__restrict__ bn_scale, const float *__restrict__ bn_shift, float *__restrict__ h1,
-                   float *__restrict__ h1_tf32) {
+                   float *__restrict__ h1_tf32, int ft_is_tf32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int KP = round_up(n, 8), MP = round_up(n, 16);
     float *Fs = reinterpret_cast<float *>(smem_raw);          // [KP][FS_LD] tf32-rounded ft rows of the star
-    float *ELs = Fs + (size_t)KP * FS_LD;                     // [KP][8]  el*log2e   (dead slots: -inf)
-    float *ERs = ELs + (size_t)KP * H_;                       // [MP][8]  er*log2e   (dead slots: 0)
+    float *ELs = Fs + (size_t)KP * FS_LD;                     // [KP][8]  el (log2 domain; dead slots: -inf)
+    float *ERs = ELs + (size_t)KP * H_;                       // [MP][8]  er (log2 domain; dead slots: 0)
     float *TM1 = ERs + (size_t)MP * H_;                       // [8] max over the star
     float *TM2 = TM1 + H_;                                    // [8] second max
     int *TA1 = reinterpret_cast<int *>(TM2 + H_);             // [8] arg of the max
@@ -284,34 +292,37 @@ gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict_
 
     // ---- stage the star of vertex i (slot k <-> TSP edge {i,k}) with cp.async: every row of the star
     // is in flight at once, so the CTA pays one L2 latency instead of one per row
+    int *NODE = TA1 + H_;                                     // [KP] line-graph node of slot k, -1 for dead slots
+    for (int k = threadIdx.x; k < KP; k += STAR_THREADS) NODE[k] = (k < n && k != i) ? kn_node(i, k, n) : -1;
+    __syncthreads();
     for (int idx = threadIdx.x; idx < KP * 32; idx += STAR_THREADS) {
         const int k = idx >> 5, q = idx & 31;                 // 16-byte piece q of row k
+        const int node = NODE[k];
         float *dst = Fs + (size_t)k * FS_LD + 4 * q;
-        if (k < n && k != i) cp_async16(dst, ft + (node0 + kn_node(i, k, n)) * D_ + 4 * q);
+        if (node >= 0) cp_async16(dst, ft + (node0 + node) * D_ + 4 * q);
         else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int idx = threadIdx.x; idx < KP * 4; idx += STAR_THREADS) {
+    for (int idx = threadIdx.x; idx < MP * 4; idx += STAR_THREADS) {
         const int k = idx >> 2, q = idx & 3;                  // el row = 2 pieces, er row = 2 pieces
-        if (k < n && k != i) {
-            const int64_t node = node0 + kn_node(i, k, n);
-            if (q < 2) cp_async16(ELs + k * H_ + 4 * q, el + node * H_ + 4 * q);
-            else cp_async16(ERs + k * H_ + 4 * (q - 2), er + node * H_ + 4 * (q - 2));
+        const int node = k < KP ? NODE[k] : -1;
+        if (node >= 0) {
+            if (q < 2) cp_async16(ELs + k * H_ + 4 * q, el + (node0 + node) * H_ + 4 * q);
+            else cp_async16(ERs + k * H_ + 4 * (q - 2), er + (node0 + node) * H_ + 4 * (q - 2));
+        } else {                                              // dead slots: weight 0 as a source, unused as a destination
+            const float fill = q < 2 ? -INFINITY : 0.f;
+            if (q >= 2 || k < KP)
+                *reinterpret_cast<float4 *>((q < 2 ? ELs : ERs) + k * H_ + 4 * (q & 1)) = make_float4(fill, fill, fill, fill);
         }
     }
     cp_async_wait_all();
     __syncthreads();
-    // in place: ft -> TF32 (round to nearest; the tensor core would otherwise truncate), el/er -> log2 domain
-    for (int idx = threadIdx.x; idx < KP * 32; idx += STAR_THREADS) {
-        float4 *ptr = reinterpret_cast<float4 *>(Fs + (size_t)(idx >> 5) * FS_LD + 4 * (idx & 31));
-        *ptr = tf32_round4(*ptr);
+    if (!ft_is_tf32) {                                        // producer did not round: the tensor core would truncate
+        for (int idx = threadIdx.x; idx < KP * 32; idx += STAR_THREADS) {
+            float4 *ptr = reinterpret_cast<float4 *>(Fs + (size_t)(idx >> 5) * FS_LD + 4 * (idx & 31));
+            *ptr = tf32_round4(*ptr);
+        }
+        __syncthreads();
     }
-    for (int idx = threadIdx.x; idx < MP * H_; idx += STAR_THREADS) {
-        const int k = idx >> 3;
-        const bool live = (k < n) && (k != i);
-        if (idx < KP * H_) ELs[idx] = live ? ELs[idx] * kLog2e : -INFINITY;
-        ERs[idx] = live ? ERs[idx] * kLog2e : 0.f;
-    }
-    __syncthreads();
 
     // ---- per-head top-2 of el over the star (warp w <-> head w)
     {
@@ -338,7 +349,12 @@ gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict_
     c.n = n; c.i = i; c.b = b; c.hd = warp; c.g = lane >> 2; c.t = lane & 3;
     c.m1 = TM1[warp]; c.m2 = TM2[warp]; c.a1 = TA1[warp];
     c.Fh = Fs + warp * 16; c.ELs = ELs; c.ERs = ERs; c.ksteps = KP / 8;
-    c.pnum = pnum; c.pden = pden; c.pmax = pmax;
+    {
+        const int64_t prow = ((int64_t)b * n + i) * n;
+        c.pn = pnum + prow * D_ + warp * 16 + 2 * c.t;
+        c.pd = pden + prow * H_ + warp;
+        c.pm = pmax + prow * H_ + warp;
+    }
     const int MT = MP / 16;
     int mt = 0;
     for (; mt + 2 <= MT; mt += 2) star_tiles<2>(c, mt);
@@ -438,8 +454,8 @@ extern "C" size_t gnngls_gat_kn_workspace_bytes(int B, int n) {
 
 extern "C" int gnngls_gat_aggregate_kn(int B, int n, const float *ft, const float *el, const float *er,
                                        const float *h, const float *gat_bias, const float *bn_scale,
-                                       const float *bn_shift, float *h1, float *h1_tf32, void *workspace,
-                                       size_t workspace_bytes, void *stream) {
+                                       const float *bn_shift, float *h1, float *h1_tf32, int ft_is_tf32,
+                                       void *workspace, size_t workspace_bytes, void *stream) {
     GNNGLS_REQUIRE(ft && el && er && h && bn_scale && bn_shift && h1, GNNGLS_ERR_BAD_ARG, "null pointer argument");
     GNNGLS_REQUIRE(n >= 3, GNNGLS_ERR_UNSUPPORTED, "line graph of K_n needs n >= 3 (got %d)", n);
     if (B <= 0) return GNNGLS_OK;
@@ -459,7 +475,7 @@ extern "C" int gnngls_gat_aggregate_kn(int B, int n, const float *ft, const floa
     if (smem > 48 * 1024)
         GNNGLS_CUDA_OK(cudaFuncSetAttribute(gat_kn_star_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gat_kn_star_kernel<<<B * n, STAR_THREADS, smem, st>>>(n, ft, el, er, pnum, pden, pmax, arrive, h, gat_bias,
-                                                          bn_scale, bn_shift, h1, h1_tf32);
+                                                          bn_scale, bn_shift, h1, h1_tf32, ft_is_tf32);
     GNNGLS_LAUNCH_OK("gat_kn_star_kernel");
     return GNNGLS_OK;
 }

@@ -134,7 +134,8 @@ def _gat_block(G, h_op, skip, Wfc, al, ar, bias, bn_scale, bn_shift, dense_impl,
         wk = _buf(ws, 'gat_ws', (nbytes,), torch.uint8, dev)
         with stage('gat_kn'):
             _lib.check(lib.gnngls_gat_aggregate_kn(G.batch_size, G.n, p(ft), p(el), p(er), p(skip), p(bias),
-                                                   p(bn_scale), p(bn_shift), p(h1), p(h1r), p(wk), nbytes, st))
+                                                   p(bn_scale), p(bn_shift), p(h1), p(h1r), 1 if tc else 0, p(wk), nbytes,
+                                                   st))
     else:
         indptr, indices = G.csr()
         with stage('gat_csr'):

@@ -154,7 +154,10 @@ typedef enum gnngls_dense_impl {
 } gnngls_dense_impl;
 
 /* GATConv.fc + attention scores (Appendix A of SURVEY.md):
- *   ft[M,128] = h * Wfc[128,128]^T ; el[M,8] = sum_f ft*attn_l ; er[M,8] = sum_f ft*attn_r       */
+ *   ft[M,128] = h * Wfc[128,128]^T ; el[M,8] = log2(e) * sum_f ft*attn_l ; er[M,8] = log2(e) * sum_f ft*attn_r
+ * The scores are stored in the log2 domain because the aggregates evaluate the edge softmax with ex2;
+ * leaky_relu is positively homogeneous so softmax(leaky_relu(el+er)) is unchanged.  On the tcgen05 path
+ * ft is stored rounded to TF32 (its only consumer is the aggregate's tensor-core operand).          */
 int gnngls_fc_forward(int impl, const float *h, int64_t M, const float *Wfc, const float *attn_l,
                       const float *attn_r, float *ft, float *el, float *er, void *stream);
 
@@ -180,8 +183,8 @@ int gnngls_gat_aggregate_csr(const int32_t *indptr, const int32_t *indices, int6
 size_t gnngls_gat_kn_workspace_bytes(int B, int n);
 int gnngls_gat_aggregate_kn(int B, int n, const float *ft, const float *el, const float *er,
                             const float *h, const float *gat_bias, const float *bn_scale,
-                            const float *bn_shift, float *h1, float *h1_tf32, void *workspace,
-                            size_t workspace_bytes, void *stream);
+                            const float *bn_shift, float *h1, float *h1_tf32, int ft_is_tf32,
+                            void *workspace, size_t workspace_bytes, void *stream);
 
 /* feed-forward block (models.py:28-35):
  *   h_out = BN2(h1 + W2 * relu(W1 * h1 + b1) + b2),  W1[512,128], W2[128,512]

@@ -140,8 +140,9 @@ def test_dense_kernels_against_tf32_rounded_oracle():
             ft64 = hh.double() @ Wd.double().t()
             el64 = (ft64.view(M, 8, 16) * al.double().view(1, 8, 16)).sum(-1)
             er64 = (ft64.view(M, 8, 16) * ar.double().view(1, 8, 16)).sum(-1)
-            assert (ft.cpu().double() - ft64).abs().max() < 1e-4, (M, impl)
-            assert (el.cpu().double() - el64).abs().max() < 1e-4 and (er.cpu().double() - er64).abs().max() < 1e-4
+            assert (ft.cpu().double() - ft64).abs().max() < (2e-3 if tc else 1e-4), (M, impl)    # tc: ft stored TF32-rounded
+            LOG2E = 1.4426950408889634      # scores are stored in the log2 domain (include/gnngls_b200.h)
+            assert (el.cpu().double() - LOG2E * el64).abs().max() < 2e-4 and (er.cpu().double() - LOG2E * er64).abs().max() < 2e-4
             nbytes = lib.gnngls_ff_workspace_bytes(impl, M)
             ws = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
             out = torch.empty(M, 128, device='cuda')

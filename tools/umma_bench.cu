@@ -18,7 +18,12 @@ __device__ __forceinline__ void mma_bf16(uint32_t d, uint64_t a, uint64_t b, uin
                  ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
-template <int N, bool BF16>
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+                 ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+
+template <int N, bool BF16, bool TMEM_A = false>
 __global__ void __launch_bounds__(128, 1) bench(long long *out, int iters, int kblocks) {
     extern __shared__ unsigned char raw[];
     unsigned char *smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
@@ -53,7 +58,8 @@ __global__ void __launch_bounds__(128, 1) bench(long long *out, int iters, int k
                         const uint64_t da = desc(a0 + (kb & 3) * 16384), db = desc(b0 + (kb & 3) * (N * 128));
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            if (BF16) mma_bf16(tm, da + 2 * k, db + 2 * k, idesc, (it | kb | k) != 0);
+                            if (TMEM_A) mma_ts(tm, tm + 256 + (kb & 3) * 32 + 8 * k, db + 2 * k, idesc, (it | kb | k) != 0);
+                            else if (BF16) mma_bf16(tm, da + 2 * k, db + 2 * k, idesc, (it | kb | k) != 0);
                             else mma(tm, da + 2 * k, db + 2 * k, idesc, (it | kb | k) != 0);
                         }
                     }
@@ -73,17 +79,17 @@ __global__ void __launch_bounds__(128, 1) bench(long long *out, int iters, int k
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
 }
 
-template <int N, bool BF16>
+template <int N, bool BF16, bool TMEM_A = false>
 void run(const char *name, int grid) {
     long long *d;
     cudaMalloc(&d, sizeof(long long) * 2 * grid);
-    auto k = bench<N, BF16>;
+    auto k = bench<N, BF16, TMEM_A>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     k<<<grid, 128, 200 * 1024>>>(d, 64, 4);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[2];
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-    printf("%-10s N=%3d grid=%3d: %s  cycles=%lld  mmas=%lld  cycles/mma=%.1f  MAC/clk/SM=%.0f\n", name, N, grid,
+    printf("%-12s N=%3d grid=%3d: %s  cycles=%lld  mmas=%lld  cycles/mma=%.1f  MAC/clk/SM=%.0f\n", name, N, grid,
            cudaGetErrorString(e), h[0], h[1], (double)h[0] / h[1], 128.0 * N * (BF16 ? 16 : 8) * h[1] / h[0]);
     cudaFree(d);
 }
@@ -92,6 +98,7 @@ int main() {
     for (int grid : {1, 148}) {
         run<32, false>("tf32", grid); run<64, false>("tf32", grid); run<128, false>("tf32", grid); run<256, false>("tf32", grid);
         run<32, true>("bf16", grid); run<128, true>("bf16", grid); run<256, true>("bf16", grid);
+        run<32, false, true>("tf32 A=tmem", grid); run<64, false, true>("tf32 A=tmem", grid); run<128, false, true>("tf32 A=tmem", grid);
     }
     return 0;
 }
