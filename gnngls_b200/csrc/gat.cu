@@ -43,6 +43,10 @@ __device__ __forceinline__ float lrelu(float s) { return fmaxf(s, kSlope * s); }
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
+// the 128-byte line at `p` will not be read again: a dirty copy in L2 need not be written back
+__device__ __forceinline__ void discard_l2_128(const void *p) {
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float4 tf32_round4(float4 v) {
     return make_float4(__uint_as_float(tf32_bits(v.x)), __uint_as_float(tf32_bits(v.y)),
@@ -397,6 +401,7 @@ gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict_
         float4 n1[FIN_U], n2[FIN_U], hv[FIN_U];
         float x1[FIN_U], x2[FIN_U], d1[FIN_U], d2[FIN_U];
         int64_t v[FIN_U];
+        int jj[FIN_U];
         bool ok[FIN_U];
 #pragma unroll
         for (int u = 0; u < FIN_U; ++u) {
@@ -410,10 +415,17 @@ gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict_
             x1[u] = __ldcg(pmax + p1 * H_ + hh); x2[u] = __ldcg(pmax + p2 * H_ + hh);
             d1[u] = __ldcg(pden + p1 * H_ + hh); d2[u] = __ldcg(pden + p2 * H_ + hh);
             hv[u] = *reinterpret_cast<const float4 *>(h + v[u] * D_ + 4 * lane);
+            jj[u] = j;
         }
 #pragma unroll
         for (int u = 0; u < FIN_U; ++u) {
             if (!ok[u]) continue;
+            // both partial rows are dead now (each is read exactly once): drop their dirty L2 lines instead of
+            // writing 1 KB per destination back to HBM
+            if (lane < 8) {
+                const int a = lane < 4 ? i : jj[u], c2 = lane < 4 ? jj[u] : i;      // rows (star a, destination c2) of pnum
+                discard_l2_128(pnum + (((int64_t)b * n + a) * n + c2) * D_ + (lane & 3) * 32);
+            }
             const float mx = fmaxf(x1[u], x2[u]);
             const float s1 = ex2(x1[u] - mx), s2 = ex2(x2[u] - mx);
             const float inv = 1.f / fmaf(d1[u], s1, d2[u] * s2);
