@@ -9,6 +9,7 @@
 // Reference lines followed (relative to the reference repository root):
 //   gnngls/operators.py:6-147, gnngls/algorithms.py:9-18,111-195, gnngls/__init__.py:17-21.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include "common.h"
 
@@ -682,7 +683,9 @@ int launch_moves(int op, bool o2a, const double *D, int64_t stride, const int *t
     const size_t staged = smem_layout(n, true, false, false, nullptr, nullptr);
     const size_t plain = smem_layout(n, false, false, false, nullptr, nullptr);
     const size_t limit = (size_t)gnngls::device_max_optin_smem();
-    if (staged <= limit) {
+    // One sweep per instance does not amortise staging an n x n fp64 matrix into shared memory (measured: 6x slower at
+    // n=100); stage only a matrix shared by the whole batch.  local_search / GLS, which sweep many times, always stage.
+    if (stride == 0 && staged <= limit) {
         if (int rc = ensure_smem(moves_kernel<true>, staged)) return rc;
         moves_kernel<true><<<grid_for(B), threads, staged, st>>>(op, o2a, D, stride, tours, pos, B, n, fi, out_delta,
                                                                 out_move, out_tours);
@@ -755,10 +758,19 @@ extern "C" int gnngls_gls_batch(const gnngls_gls_args *args, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GlsDev P;
     P.a = a;
-    const int threads = pick_threads(a.n);
+    int threads = pick_threads(a.n);
+    { const char *e = getenv("GNNGLS_GLS_THREADS"); if (e && atoi(e) >= 32) threads = atoi(e); }   // experiment switch
     const size_t staged = smem_layout(a.n, true, true, true, nullptr, nullptr);
     const size_t plain = smem_layout(a.n, false, true, false, nullptr, nullptr);
-    if (staged <= (size_t)gnngls::device_max_optin_smem()) {
+    // Tier choice.  With D (fp64) + penalties staged in shared memory only 2 CTAs fit per SM at n=100; reading them
+    // through L1/L2 instead lets 8 CTAs share an SM, which measured ~10% faster for this latency-bound loop
+    // (profiles/r1_gls_tiers.md).  The global tier needs the caller's int32 penalties buffer; GNNGLS_GLS_TIER=staged|global
+    // overrides.
+    static int tier = -1;                                      // 0 auto, 1 staged, 2 global
+    if (tier < 0) { const char *e = getenv("GNNGLS_GLS_TIER"); tier = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'g' ? 2 : 0)); }
+    const bool fits = staged <= (size_t)gnngls::device_max_optin_smem();
+    const bool use_global = a.penalties && (tier == 2 || (tier == 0 && a.n >= 64)) ;
+    if (fits && !use_global) {
         if (int rc = ensure_smem(gls_kernel<true>, staged)) return rc;
         gls_kernel<true><<<grid_for(a.B), threads, staged, st>>>(P);
     } else {

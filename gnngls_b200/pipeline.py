@@ -105,7 +105,8 @@ class RegretGLS:
                     mats.append(regret_matrix(regret, n))
             gl, kind = torch.stack(mats, 1).contiguous(), _ops.GUIDE_MATRIX_F64
             init_tours, init_costs = _ops.nn_init(gl[:, 0].contiguous(), kind, D, 0)
-        state = _ops.GlsState(D, gl.contiguous(), kind, init_tours, init_costs, keep_penalties=False)
+        # a penalties buffer lets the GLS kernel pick its L2-resident tier (faster for n >= 64, see csrc/search.cu)
+        state = _ops.GlsState(D, gl.contiguous(), kind, init_tours, init_costs, keep_penalties=n >= 64)
         with stage('gls'):
             info = _ops.gls_run(state, n_iters, perturbation_moves, False, 0, want_counters=True)
         return SolveResult(state.best_tours, state.best_costs, init_costs, regret if keep_regret else None,

@@ -191,3 +191,41 @@ def test_pipeline_tours_bit_exact_given_gpu_regrets():
     assert np.array_equal(_golden.bits(res.best_costs.cpu().numpy()), _golden.bits(o_c))
     t_h, c_h = solver.solve_host(D, chunk=10, n_iters=K, perturbation_moves=20)
     assert np.array_equal(t_h, o_t) and np.array_equal(_golden.bits(c_h), _golden.bits(o_c))
+
+
+@pytest.mark.parametrize('n,B', [(3, 4), (4, 3), (7, 2), (33, 2), (100, 1)])
+def test_model_sizes_vs_fp64_oracle(n, B):
+    """Smallest legal graphs (n=3: every node has 2 in-edges), odd sizes that exercise every padding path of the
+    star kernel (n not a multiple of 8/16) and one full-size TSP100 instance."""
+    port, m = make_models()
+    _, D = instances.random_instances(B, n, seed=100 + n)
+    x = (instances.edge_features(D) / np.float32(np.sqrt(2))).reshape(-1, 1)
+    with torch.no_grad():
+        y64 = port.double()(model_port.EdgeListGraph.kn_line_graph(n, B), torch.as_tensor(x).double()).numpy()
+    port.float()
+    tol = tf32_budget(port, n, B, x, y64)
+    for dense, gat in (('tcgen05', 'kn'), ('tcgen05', 'csr')):
+        err = np.abs(run(m, n, B, x, dense, gat) - y64).max()
+        print(f'n={n} B={B} {dense}+{gat}: err={err:.3e} tol={tol:.3e}')
+        assert err <= tol
+    assert np.abs(run(m, n, B, x, 'simt', 'csr') - y64).max() <= REL_FP32 * np.abs(y64).max()
+
+
+def test_public_layer_and_gatconv_forward():
+    """AttentionLayer.forward(G, x) and GATConv.forward(G, feat) keep the reference call signatures (models.py:38,12)."""
+    port, m = make_models()
+    n, B = 9, 2
+    G = graph.LineGraph.complete(n, B, 'cuda')
+    g = model_port.EdgeListGraph.kn_line_graph(n, B)
+    torch.manual_seed(3)
+    h = torch.randn(G.number_of_nodes(), 128)
+    layer, player = m.message_passing_layers[2], port.message_passing_layers[2]
+    with torch.no_grad():
+        want = player.double()(g, h.double()).float()
+        got = layer(G, h.cuda()).cpu()
+        gat_want = player.message_passing.module(g, h.double()).float()
+        gat_got = layer.message_passing.module(G, h.cuda()).cpu()
+    port.float()
+    assert got.shape == want.shape and (got - want).abs().max() < 2e-2 * want.abs().max()
+    assert gat_got.shape == gat_want.shape == (G.number_of_nodes(), 8, 16)
+    assert (gat_got - gat_want).abs().max() < 2e-2 * gat_want.abs().max()
