@@ -553,7 +553,8 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 template <int CL>      // CTAs per cluster sharing (multicasting) the streamed weights: 1, 2 or 4
 __global__ void __launch_bounds__(FF_THREADS, 1)
 ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
-                     const __grid_constant__ CUtensorMap tmW2, const EpiParams p, const float *__restrict__ b1) {
+                     const __grid_constant__ CUtensorMap tmW2, const EpiParams p, const float *__restrict__ b1,
+                     const int round_a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024B-aligned, still .shared
     unsigned char *sA = smem;
@@ -637,7 +638,8 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const unsigned char *row = sA + kb * (BM * BK * 4) + r * 128;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 x = *reinterpret_cast<const float4 *>(row + ((j ^ (r & 7)) << 4));
+                    float4 x = *reinterpret_cast<const float4 *>(row + ((j ^ (r & 7)) << 4));
+                    if (round_a) x = tf32_rna4(x);            // operand is the raw fp32 activation: round here, not truncate in the MMA
                     v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
                 }
                 tmem_st_32x32(tm_a + lane_sel + kb * BK, v);
@@ -785,7 +787,8 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 template <int CL>
-int launch_ff_fused_cl(const float *a_op, const float *W1, const float *b1, const float *W2, const EpiParams &p, cudaStream_t st) {
+int launch_ff_fused_cl(const float *a_op, int round_a, const float *W1, const float *b1, const float *W2, const EpiParams &p,
+                       cudaStream_t st) {
     CUtensorMap tmA, tmW1, tmW2;
     if (int rc = make_map(&tmA, a_op, (uint64_t)p.M, D_, BM)) return rc;
     if (int rc = make_map(&tmW1, W1, HID_, D_, CL == 1 ? FF_HC : 128 / CL)) return rc;     // box [rows x 32 k]
@@ -807,21 +810,22 @@ int launch_ff_fused_cl(const float *a_op, const float *W1, const float *b1, cons
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GNNGLS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmW1, tmW2, p, b1));
+    GNNGLS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmW1, tmW2, p, b1, round_a));
     GNNGLS_LAUNCH_OK("ff_fused_tf32_kernel");
     return GNNGLS_OK;
 }
 
-int launch_ff_fused(const float *a_op, const float *W1, const float *b1, const float *W2, const EpiParams &p, cudaStream_t st) {
-    static int cl = -1;                                       // GNNGLS_FF_CLUSTER = 1 | 2 | 4 (default 2)
+int launch_ff_fused(const float *a_op, int round_a, const float *W1, const float *b1, const float *W2, const EpiParams &p,
+                    cudaStream_t st) {
+    static int cl = -1;                                       // GNNGLS_FF_CLUSTER = 1 | 2 | 4 (default 1)
     if (cl < 0) {
         const char *e = getenv("GNNGLS_FF_CLUSTER");
-        cl = e ? atoi(e) : 2;
-        if (cl != 1 && cl != 2 && cl != 4) cl = 2;
+        cl = e ? atoi(e) : 1;      // multicast measured neutral at 2, slower at 4 (profiles/r1_ff_cluster.md): default off
+        if (cl != 1 && cl != 2 && cl != 4) cl = 1;
     }
-    if (cl == 1) return launch_ff_fused_cl<1>(a_op, W1, b1, W2, p, st);
-    if (cl == 4) return launch_ff_fused_cl<4>(a_op, W1, b1, W2, p, st);
-    return launch_ff_fused_cl<2>(a_op, W1, b1, W2, p, st);
+    if (cl == 1) return launch_ff_fused_cl<1>(a_op, round_a, W1, b1, W2, p, st);
+    if (cl == 4) return launch_ff_fused_cl<4>(a_op, round_a, W1, b1, W2, p, st);
+    return launch_ff_fused_cl<2>(a_op, round_a, W1, b1, W2, p, st);
 }
 
 // ================================================================================================
@@ -977,7 +981,7 @@ extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32
         static int dbg = -1;                                   // GNNGLS_FF_DEBUG: timing experiments only (wrong results!)
         if (dbg < 0) { const char *e = getenv("GNNGLS_FF_DEBUG"); dbg = e ? atoi(e) : 0; }
         p2.round_tf32 = dbg;
-        return launch_ff_fused(a1, W1, b1, W2, p2, st);
+        return launch_ff_fused(a1, h1_tf32 == nullptr, W1, b1, W2, p2, st);      // no pre-rounded copy: round while staging
     }
     if (impl == GNNGLS_DENSE_SIMT) {
         if (int rc = launch_simt_gemm<HID_, D_, EPI_FF1>(a1, W1, p1, st)) return rc;

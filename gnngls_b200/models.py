@@ -122,7 +122,7 @@ def _gat_block(G, h_op, skip, Wfc, al, ar, bias, bn_scale, bn_shift, dense_impl,
     el = _buf(ws, 'el', (M, 8), torch.float32, dev)
     er = _buf(ws, 'er', (M, 8), torch.float32, dev)
     h1 = _buf(ws, 'h1', (M, 128), torch.float32, dev)
-    h1r = _buf(ws, 'h1_tf32', (M, 128), torch.float32, dev) if tc else None
+    h1r = None      # the fused FF kernel rounds h1 to TF32 itself while staging it into tensor memory
     p = _ops._ptr
     with stage('fc'):
         _lib.check(lib.gnngls_fc_forward(dense_impl, p(h_op), M, p(Wfc), p(al), p(ar), p(ft), p(el), p(er), st))

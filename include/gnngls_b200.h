@@ -188,7 +188,8 @@ int gnngls_gat_aggregate_kn(int B, int n, const float *ft, const float *el, cons
 
 /* feed-forward block (models.py:28-35):
  *   h_out = BN2(h1 + W2 * relu(W1 * h1 + b1) + b2),  W1[512,128], W2[128,512]
- * h1_tf32 (nullable) is the operand of the first contraction; the skip always reads h1.
+ * h1_tf32 (nullable) is a pre-rounded operand copy for the first contraction; when NULL the tensor-core
+ * kernel rounds h1 to TF32 itself while staging the tile into tensor memory.  The skip always reads h1.
  * `workspace` must hold gnngls_ff_workspace_bytes(impl, M) bytes (may be 0). */
 size_t gnngls_ff_workspace_bytes(int impl, int64_t M);
 int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32, int64_t M, const float *W1,

@@ -156,6 +156,12 @@ def test_dense_kernels_against_tf32_rounded_oracle():
             o64 = (hh.double() + hid @ W2d.double().t() + b2.double()) * sc.double() + sh.double()
             assert (out.cpu().double() - o64).abs().max() < (1e-3 if tc else 2e-4), (M, impl)
             assert torch.equal(out_r.cpu(), models.tf32_round(out.cpu()))
+            if tc:      # no pre-rounded operand copy: the kernel rounds h while staging, the skip stays unrounded fp32
+                hraw = h.cuda()
+                _lib.check(lib.gnngls_ff_forward(impl, p(hraw), None, M, p(W1c), p(b1c), p(W2c), p(b2c), p(scc), p(shc), p(out),
+                                                 None, p(ws), nbytes, _ops._stream()))
+                o64b = (h.double() + hid @ W2d.double().t() + b2.double()) * sc.double() + sh.double()
+                assert (out.cpu().double() - o64b).abs().max() < 1e-3, (M, 'round-in-kernel')
 
 
 def test_glue_kernels_bit_exact():
