@@ -220,7 +220,6 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -620,7 +619,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int c2 = 0; c2 < BN / 32; ++c2) {
                 float v[32];
                 tmem_ld_32x32(tm_d2 + lane_sel + d * BN + c2 * 32, v);
-                if (!(p.round_tf32 & 2)) epilogue_tile32<EPI_FF2>(p, svec, stg, w * BM + q * 32, c2 * 32, v, lane);
+                epilogue_tile32<EPI_FF2>(p, svec, stg, w * BM + q * 32, c2 * 32, v, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -698,7 +697,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint32_t tm_acc = tm_d2 + d * BN;
             auto gemm2 = [&](int c) {
                 const int g = c & 1;
-                if (!(p.round_tf32 & 1)) { mbar_wait(&h_full[g], n_h[g] & 1); } ++n_h[g];  // epilogue-1 has rewritten DH[g] with the hidden chunk
+                mbar_wait(&h_full[g], n_h[g] & 1); ++n_h[g];  // epilogue-1 has rewritten DH[g] with the hidden chunk
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     mbar_wait(&w_full[stage], phase);
@@ -977,12 +976,8 @@ extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32
     EpiParams p2{};
     p2.M = M; p2.out = h_out; p2.out_tf32 = h_out_tf32; p2.v0 = b2; p2.v1 = bn_scale; p2.v2 = bn_shift; p2.skip = h1;
     const float *a1 = h1_tf32 ? h1_tf32 : h1;                 // GEMM operand; the skip path always reads fp32 h1
-    if (impl == GNNGLS_DENSE_TCGEN05) {
-        static int dbg = -1;                                   // GNNGLS_FF_DEBUG: timing experiments only (wrong results!)
-        if (dbg < 0) { const char *e = getenv("GNNGLS_FF_DEBUG"); dbg = e ? atoi(e) : 0; }
-        p2.round_tf32 = dbg;
+    if (impl == GNNGLS_DENSE_TCGEN05)
         return launch_ff_fused(a1, h1_tf32 == nullptr, W1, b1, W2, p2, st);      // no pre-rounded copy: round while staging
-    }
     if (impl == GNNGLS_DENSE_SIMT) {
         if (int rc = launch_simt_gemm<HID_, D_, EPI_FF1>(a1, W1, p1, st)) return rc;
         return launch_simt_gemm<D_, HID_, EPI_FF2>(hid, W2, p2, st);

@@ -758,8 +758,7 @@ extern "C" int gnngls_gls_batch(const gnngls_gls_args *args, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GlsDev P;
     P.a = a;
-    int threads = pick_threads(a.n);
-    { const char *e = getenv("GNNGLS_GLS_THREADS"); if (e && atoi(e) >= 32) threads = atoi(e); }   // experiment switch
+    const int threads = pick_threads(a.n);
     const size_t staged = smem_layout(a.n, true, true, true, nullptr, nullptr);
     const size_t plain = smem_layout(a.n, false, true, false, nullptr, nullptr);
     // Tier choice.  With D (fp64) + penalties staged in shared memory only 2 CTAs fit per SM at n=100; reading them
