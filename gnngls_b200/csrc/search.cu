@@ -8,6 +8,7 @@
 //
 // Reference lines followed (relative to the reference repository root):
 //   gnngls/operators.py:6-147, gnngls/algorithms.py:9-18,111-195, gnngls/__init__.py:17-21.
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -495,7 +496,7 @@ __global__ void gls_kernel(const GlsDev P) {
                     const double pen = STAGED ? (double)s.pen[x * n + y] : (double)pen_g[x * n + y];
                     const double util = __ddiv_rn(guide(x, y), __dadd_rn(1.0, pen));
                     // reuse the min-reduction on the negated utility: min(-util), ties -> smaller p
-                    const double neg = -util;
+                    const double neg = (util != util) ? INFINITY : -util;       // NaN guide: never the arg-max
                     if (u.key < 0 || neg < u.delta) { u.delta = neg; u.key = p; }
                 }
                 u = block_reduce_best(u, false, s.red);
@@ -595,7 +596,8 @@ __global__ void nn_init_kernel(int guide_kind, const void *guides, const double 
             int bj = -1;
             for (int q = 0, j = lane; j < n; ++q, j += 32) {
                 if (visited & (1u << q)) continue;
-                const double w = g(cur, j);
+                double w = g(cur, j);
+                if (w != w) w = INFINITY;                      // NaN guide values: keep the comparison a total order
                 if (bj < 0 || w < bw) { bw = w; bj = j; }      // ascending j per lane: first minimum kept
             }
 #pragma unroll
