@@ -41,7 +41,7 @@ def parse():
                     help='shard per GPU; 12,500 x 8 GPUs = the 100k-instance TSP100 config of BASELINE.json')
     ap.add_argument('--gls-iters', type=int, default=10, help='GLS outer iterations K (fixed count, SURVEY 8(d))')
     ap.add_argument('--perturbation-moves', type=int, default=20)
-    ap.add_argument('--micro-batch', type=int, default=64)
+    ap.add_argument('--micro-batch', type=int, default=256)
     ap.add_argument('--chunk', type=int, default=2048, help='instances per host->device chunk in the e2e path')
     ap.add_argument('--cpu-sample', type=int, default=4, help='instances in the bounded CPU-baseline sample')
     ap.add_argument('--ref-sample', type=int, default=2, help='instances per step of the reference arm')
