@@ -88,7 +88,7 @@ class RegretGLS:
         return regret
 
     @torch.no_grad()
-    def solve(self, D, n_iters=10, perturbation_moves=20, guides=('regret_pred',), keep_regret=False):
+    def solve(self, D, n_iters=10, perturbation_moves=20, guides=('regret_pred',), keep_regret=False, max_events=0):
         """Full path for D [B,n,n] fp64 on the GPU.  guides: tuple of 'regret_pred' / 'weight'."""
         B, n = D.shape[0], D.shape[-1]
         regret = self.predict_regret(D) if 'regret_pred' in guides else None
@@ -104,13 +104,15 @@ class RegretGLS:
                 else:
                     mats.append(regret_matrix(regret, n))
             gl, kind = torch.stack(mats, 1).contiguous(), _ops.GUIDE_MATRIX_F64
-            init_tours, init_costs = _ops.nn_init(gl[:, 0].contiguous(), kind, D, 0)
+            # test.py:85-88: the initial tour follows regret_pred whenever it is among the guides, else the weight
+            nn_guide = mats[list(guides).index('regret_pred')] if 'regret_pred' in guides else D
+            init_tours, init_costs = _ops.nn_init(nn_guide.contiguous(), kind, D, 0)
         # a penalties buffer lets the GLS kernel pick its L2-resident tier (faster for n >= 64, see csrc/search.cu)
         state = _ops.GlsState(D, gl.contiguous(), kind, init_tours, init_costs, keep_penalties=n >= 64)
         with stage('gls'):
-            info = _ops.gls_run(state, n_iters, perturbation_moves, False, 0, want_counters=True)
+            info = _ops.gls_run(state, n_iters, perturbation_moves, False, max_events, want_counters=True)
         return SolveResult(state.best_tours, state.best_costs, init_costs, regret if keep_regret else None,
-                           info['counters'], info['status'])
+                           info['counters'], info['status'], {'events': info['events'], 'n_events': info['n_events']})
 
     @torch.no_grad()
     def solve_host(self, D_host, chunk=2048, **kw):
