@@ -41,10 +41,10 @@ SIGNATURES = {
     'gnngls_tour_cost_batch': (_i, [_p, _p, _i, _i, _p, _p]),
     'gnngls_edge_features': (_i, [_p, _i, _i, _d, _d, _p, _p]),
     'gnngls_embed_forward': (_i, [_p, _i64, _i, _p, _p, _p, _p, _p]),
-    'gnngls_fc_forward': (_i, [_i, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
-    'gnngls_gat_aggregate_csr': (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'gnngls_fc_forward': (_i, [_i, _p, _i64, _p, _p, _p, _p, _i, _p, _p, _p]),
+    'gnngls_gat_aggregate_csr': (_i, [_p, _p, _i64, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'gnngls_gat_kn_workspace_bytes': (_sz, [_i, _i]),
-    'gnngls_gat_aggregate_kn': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    'gnngls_gat_aggregate_kn': (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     'gnngls_ff_workspace_bytes': (_sz, [_i, _i64]),
     'gnngls_ff_forward': (_i, [_i, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     'gnngls_decision_forward': (_i, [_p, _i64, _i, _p, _p, _p, _p]),
@@ -55,7 +55,7 @@ SIGNATURES = {
 KERNELS_PER_CALL = {
     'gnngls_moves_eval_a2a': 1, 'gnngls_moves_eval_o2a': 1, 'gnngls_local_search_batch': 1, 'gnngls_gls_batch': 1,
     'gnngls_nn_init_batch': 1, 'gnngls_tour_cost_batch': 1, 'gnngls_edge_features': 1, 'gnngls_embed_forward': 1,
-    'gnngls_fc_forward': 1, 'gnngls_gat_aggregate_csr': 1, 'gnngls_gat_aggregate_kn': 1, 'gnngls_ff_forward': 2,
+    'gnngls_fc_forward': 1, 'gnngls_gat_aggregate_csr': 1, 'gnngls_gat_aggregate_kn': 2 if os.environ.get('GNNGLS_STAR_PIPELINE', '').lower().startswith('s') else 1, 'gnngls_ff_forward': 2,
     'gnngls_decision_forward': 1, 'gnngls_regret_postprocess': 1,
 }
 

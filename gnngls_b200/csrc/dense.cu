@@ -17,6 +17,7 @@
 // tests to cross-check the tensor-core path.  Also here: embed_layer and decision_layer, which
 // are K=in_dim / N=out_dim degenerate and run as fused elementwise / dot-product kernels.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdlib>
 #include "common.h"
@@ -33,6 +34,7 @@ enum { EPI_FC = 0, EPI_FF1 = 1, EPI_FF2 = 2 };
 struct EpiParams {
     int64_t M;
     float *out;          // FC: ft [M,128]; FF1: hid [M,512]; FF2: h_out [M,128]
+    __half *out_f16;     // FC only (nullable): store ft as fp16 [M,128] instead of fp32 `out`
     float *out_tf32;     // FF2 only (nullable): copy of h_out rounded to TF32 for the next tensor-core GEMM
     float *el, *er;      // FC only, [M,8]
     const float *v0;     // FC: attn_l[128]; FF1: b1[512]; FF2: b2[128]
@@ -50,6 +52,12 @@ __device__ __forceinline__ float tf32_rna(float x) {
 __device__ __forceinline__ float4 tf32_rna4(float4 v) {
     return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
 }
+// two fp32 -> packed fp16x2 (lo in the low half), round-to-nearest-even, saturating to +-65504
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 
 // Fused epilogue for 4 consecutive columns [col, col+4) of one row (SIMT debug GEMM).  Called with a
 // full warp in which lanes 4q..4q+3 hold consecutive column quads of the same row (FC reduction).
@@ -65,7 +73,8 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams &p, int64_t row, i
         sl += __shfl_xor_sync(0xffffffffu, sl, 2);
         sr += __shfl_xor_sync(0xffffffffu, sr, 2);
         if (valid) {
-            *reinterpret_cast<float4 *>(p.out + row * D_ + col) = p.round_tf32 ? tf32_rna4(acc) : acc;
+            if (p.out_f16) *reinterpret_cast<uint2 *>(p.out_f16 + row * D_ + col) = make_uint2(pack_f16x2(acc.x, acc.y), pack_f16x2(acc.z, acc.w));
+            else *reinterpret_cast<float4 *>(p.out + row * D_ + col) = p.round_tf32 ? tf32_rna4(acc) : acc;
             if ((col & 15) == 0) {   // first quad of a head: 16 columns per head
                 p.el[row * H_ + (col >> 4)] = sl * kLog2e;
                 p.er[row * H_ + (col >> 4)] = sr * kLog2e;
@@ -133,23 +142,47 @@ __device__ __forceinline__ void epilogue_tile32(const EpiParams &p, const float 
     const int64_t row = row0 + lane;
     if (EPI == EPI_FC) {
         float sl[2] = {0.f, 0.f}, sr[2] = {0.f, 0.f};       // 32 columns = two heads of 16
+        const bool f16 = p.out_f16 != nullptr;
+        // fp16 output: the tile holds this warp's 64 columns as 32 rows x 128 bytes; this call fills half of it
+        const int piece0 = (col & 32) >> 3;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 al = *reinterpret_cast<const float4 *>(sv + col + 4 * j);
             const float4 ar = *reinterpret_cast<const float4 *>(sv + D_ + col + 4 * j);
             sl[j >> 2] += v[4 * j] * al.x + v[4 * j + 1] * al.y + v[4 * j + 2] * al.z + v[4 * j + 3] * al.w;
             sr[j >> 2] += v[4 * j] * ar.x + v[4 * j + 1] * ar.y + v[4 * j + 2] * ar.z + v[4 * j + 3] * ar.w;
-            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (p.round_tf32) o = tf32_rna4(o);             // ft only feeds the aggregate's tensor-core B operand
-            *stg_slot(stg, lane, j) = o;
+            if (f16) {
+                if (j & 1) continue;
+                *reinterpret_cast<uint4 *>(stg_slot(stg, lane, piece0 + (j >> 1))) =
+                    make_uint4(pack_f16x2(v[4 * j], v[4 * j + 1]), pack_f16x2(v[4 * j + 2], v[4 * j + 3]),
+                               pack_f16x2(v[4 * j + 4], v[4 * j + 5]), pack_f16x2(v[4 * j + 6], v[4 * j + 7]));
+            } else {
+                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (p.round_tf32) o = tf32_rna4(o);         // ft only feeds the aggregate's tensor-core B operand
+                *stg_slot(stg, lane, j) = o;
+            }
         }
         if (row < p.M) {
             *reinterpret_cast<float2 *>(p.el + row * H_ + (col >> 4)) = make_float2(sl[0] * kLog2e, sl[1] * kLog2e);
             *reinterpret_cast<float2 *>(p.er + row * H_ + (col >> 4)) = make_float2(sr[0] * kLog2e, sr[1] * kLog2e);
         }
-        __syncwarp();
-        stg_store_tile(stg, p.out, nullptr, row0, col, D_, p.M, lane);
-        __syncwarp();
+        if (f16) {
+            if (col & 32) {                                 // second half staged: store 32 rows x 128 B, 4 rows per instruction
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + (lane >> 3), pc = lane & 7;
+                    if (row0 + r < p.M)
+                        *reinterpret_cast<uint4 *>(p.out_f16 + (row0 + r) * D_ + (col & ~63) + 8 * pc) =
+                            *reinterpret_cast<const uint4 *>(stg_slot(stg, r, pc));
+                }
+                __syncwarp();
+            }
+        } else {
+            __syncwarp();
+            stg_store_tile(stg, p.out, nullptr, row0, col, D_, p.M, lane);
+            __syncwarp();
+        }
     } else if (EPI == EPI_FF1) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -944,13 +977,18 @@ extern "C" int gnngls_decision_forward(const float *h, int64_t M, int out_dim, c
 }
 
 extern "C" int gnngls_fc_forward(int impl, const float *h, int64_t M, const float *Wfc, const float *attn_l,
-                                 const float *attn_r, float *ft, float *el, float *er, void *stream) {
+                                 const float *attn_r, void *ft, int ft_dtype, float *el, float *er, void *stream) {
     GNNGLS_REQUIRE(h && Wfc && attn_l && attn_r && ft && el && er, GNNGLS_ERR_BAD_ARG, "null pointer argument");
+    GNNGLS_REQUIRE(ft_dtype == GNNGLS_FT_F32 || ft_dtype == GNNGLS_FT_TF32 || ft_dtype == GNNGLS_FT_F16, GNNGLS_ERR_BAD_ARG,
+                   "unknown ft_dtype %d", ft_dtype);
     if (M <= 0) return GNNGLS_OK;
     EpiParams p{};
-    p.M = M; p.out = ft; p.el = el; p.er = er; p.v0 = attn_l; p.v1 = attn_r;
+    p.M = M; p.el = el; p.er = er; p.v0 = attn_l; p.v1 = attn_r;
+    if (ft_dtype == GNNGLS_FT_F16) p.out_f16 = static_cast<__half *>(ft);
+    else p.out = static_cast<float *>(ft);
+    p.round_tf32 = ft_dtype == GNNGLS_FT_TF32;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (impl == GNNGLS_DENSE_TCGEN05) { p.round_tf32 = 1; return launch_tc_gemm<D_, D_, EPI_FC>(h, Wfc, p, st); }
+    if (impl == GNNGLS_DENSE_TCGEN05) return launch_tc_gemm<D_, D_, EPI_FC>(h, Wfc, p, st);
     if (impl == GNNGLS_DENSE_SIMT) return launch_simt_gemm<D_, D_, EPI_FC>(h, Wfc, p, st);
     GNNGLS_REQUIRE(false, GNNGLS_ERR_BAD_ARG, "unknown dense impl %d", impl);
 }

@@ -118,14 +118,22 @@ def _gat_block(G, h_op, skip, Wfc, al, ar, bias, bn_scale, bn_shift, dense_impl,
     M, dev = h_op.shape[0], h_op.device
     st = _ops._stream()
     tc = dense_impl == _ops.DENSE_TCGEN05
-    ft = _buf(ws, 'ft', (M, 128), torch.float32, dev)
+    # tensor-core path: ft travels as fp16 (same mantissa as the TF32 operand it would be rounded to, half the
+    # bytes); GNNGLS_FT_DTYPE=tf32 keeps fp32 storage.  The fp32 debug path keeps ft exact.
+    if not tc:
+        ft_dtype = _ops.FT_F32
+    elif os.environ.get('GNNGLS_FT_DTYPE', 'f16').lower() == 'tf32':
+        ft_dtype = _ops.FT_TF32
+    else:
+        ft_dtype = _ops.FT_F16
+    ft = _buf(ws, 'ft', (M, 128), torch.float16 if ft_dtype == _ops.FT_F16 else torch.float32, dev)
     el = _buf(ws, 'el', (M, 8), torch.float32, dev)
     er = _buf(ws, 'er', (M, 8), torch.float32, dev)
     h1 = _buf(ws, 'h1', (M, 128), torch.float32, dev)
     h1r = None      # the fused FF kernel rounds h1 to TF32 itself while staging it into tensor memory
     p = _ops._ptr
     with stage('fc'):
-        _lib.check(lib.gnngls_fc_forward(dense_impl, p(h_op), M, p(Wfc), p(al), p(ar), p(ft), p(el), p(er), st))
+        _lib.check(lib.gnngls_fc_forward(dense_impl, p(h_op), M, p(Wfc), p(al), p(ar), p(ft), ft_dtype, p(el), p(er), st))
     use_kn = gat_impl == 'kn' or (gat_impl == 'auto' and G.kind == 'kn' and G.n <= 380)
     if use_kn:
         if G.kind != 'kn':
@@ -133,13 +141,12 @@ def _gat_block(G, h_op, skip, Wfc, al, ar, bias, bn_scale, bn_shift, dense_impl,
         nbytes = lib.gnngls_gat_kn_workspace_bytes(G.batch_size, G.n)
         wk = _buf(ws, 'gat_ws', (nbytes,), torch.uint8, dev)
         with stage('gat_kn'):
-            _lib.check(lib.gnngls_gat_aggregate_kn(G.batch_size, G.n, p(ft), p(el), p(er), p(skip), p(bias),
-                                                   p(bn_scale), p(bn_shift), p(h1), p(h1r), 1 if tc else 0, p(wk), nbytes,
-                                                   st))
+            _lib.check(lib.gnngls_gat_aggregate_kn(G.batch_size, G.n, p(ft), ft_dtype, p(el), p(er), p(skip), p(bias),
+                                                   p(bn_scale), p(bn_shift), p(h1), p(h1r), p(wk), nbytes, st))
     else:
         indptr, indices = G.csr()
         with stage('gat_csr'):
-            _lib.check(lib.gnngls_gat_aggregate_csr(p(indptr), p(indices), M, p(ft), p(el), p(er), p(skip), p(bias),
+            _lib.check(lib.gnngls_gat_aggregate_csr(p(indptr), p(indices), M, p(ft), ft_dtype, p(el), p(er), p(skip), p(bias),
                                                     p(bn_scale), p(bn_shift), p(h1), p(h1r), st))
     return h1, h1r
 

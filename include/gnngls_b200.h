@@ -153,13 +153,21 @@ typedef enum gnngls_dense_impl {
     GNNGLS_DENSE_SIMT = 1       /* plain fp32 CUDA-core kernel: debug cross-check only            */
 } gnngls_dense_impl;
 
+/* storage format of the projected features ft[M,128] handed from fc to the aggregates */
+typedef enum gnngls_ft_dtype {
+    GNNGLS_FT_F32 = 0,    /* fp32, unrounded (pure-fp32 debug path)                                   */
+    GNNGLS_FT_TF32 = 1,   /* fp32 storage, values rounded to TF32 (10-bit mantissa)                   */
+    GNNGLS_FT_F16 = 2     /* IEEE fp16 (same 10-bit mantissa, half the bytes; saturates at +-65504)   */
+} gnngls_ft_dtype;
+
 /* GATConv.fc + attention scores (Appendix A of SURVEY.md):
  *   ft[M,128] = h * Wfc[128,128]^T ; el[M,8] = log2(e) * sum_f ft*attn_l ; er[M,8] = log2(e) * sum_f ft*attn_r
  * The scores are stored in the log2 domain because the aggregates evaluate the edge softmax with ex2;
- * leaky_relu is positively homogeneous so softmax(leaky_relu(el+er)) is unchanged.  On the tcgen05 path
- * ft is stored rounded to TF32 (its only consumer is the aggregate's tensor-core operand).          */
+ * leaky_relu is positively homogeneous so softmax(leaky_relu(el+er)) is unchanged.  el/er are always
+ * computed from the unrounded fp32 accumulators; `ft` is stored as `ft_dtype` says (its only consumer
+ * is the aggregate, whose tensor-core operand has a 10-bit mantissa anyway).                        */
 int gnngls_fc_forward(int impl, const float *h, int64_t M, const float *Wfc, const float *attn_l,
-                      const float *attn_r, float *ft, float *el, float *er, void *stream);
+                      const float *attn_r, void *ft, int ft_dtype, float *el, float *er, void *stream);
 
 /* Per-channel affine form of eval-mode BatchNorm1d: y = x*scale + shift
  * (scale = gamma/sqrt(var+eps), shift = beta - mean*scale; models.py:27,35).
@@ -173,7 +181,7 @@ int gnngls_fc_forward(int impl, const float *h, int64_t M, const float *Wfc, con
 /* GAT aggregate over an arbitrary destination-sorted CSR graph + skip + BatchNorm1 (models.py:12-15,27):
  *   h1[v] = BN1(h[v] + sum_u softmax_u(leaky_relu(el[u]+er[v])) ft[u] + gat_bias)               */
 int gnngls_gat_aggregate_csr(const int32_t *indptr, const int32_t *indices, int64_t M,
-                             const float *ft, const float *el, const float *er, const float *h,
+                             const void *ft, int ft_dtype, const float *el, const float *er, const float *h,
                              const float *gat_bias /* [128] or NULL */, const float *bn_scale,
                              const float *bn_shift, float *h1, float *h1_tf32, void *stream);
 
@@ -181,9 +189,9 @@ int gnngls_gat_aggregate_csr(const int32_t *indptr, const int32_t *indices, int6
  * (neighbours of (i,j) are (i,k) and (k,j)); M = B*n(n-1)/2.  `workspace` must hold
  * gnngls_gat_kn_workspace_bytes(B,n) bytes. */
 size_t gnngls_gat_kn_workspace_bytes(int B, int n);
-int gnngls_gat_aggregate_kn(int B, int n, const float *ft, const float *el, const float *er,
+int gnngls_gat_aggregate_kn(int B, int n, const void *ft, int ft_dtype, const float *el, const float *er,
                             const float *h, const float *gat_bias, const float *bn_scale,
-                            const float *bn_shift, float *h1, float *h1_tf32, int ft_is_tf32,
+                            const float *bn_shift, float *h1, float *h1_tf32,
                             void *workspace, size_t workspace_bytes, void *stream);
 
 /* feed-forward block (models.py:28-35):

@@ -134,15 +134,22 @@ def test_dense_kernels_against_tf32_rounded_oracle():
             W1d, W2d = (models.tf32_round(W1), models.tf32_round(W2)) if tc else (W1, W2)
             hd, Wc, alc, arc = hh.cuda(), Wd.cuda(), al.cuda(), ar.cuda()      # keep device copies alive
             W1c, b1c, W2c, b2c, scc, shc = W1d.cuda(), b1.cuda(), W2d.cuda(), b2.cuda(), sc.cuda(), sh.cuda()
-            ft = torch.empty(M, 128, device='cuda'); el = torch.empty(M, 8, device='cuda'); er = torch.empty(M, 8, device='cuda')
-            _lib.check(lib.gnngls_fc_forward(impl, p(hd), M, p(Wc), p(alc), p(arc), p(ft), p(el), p(er),
-                                             _ops._stream()))
+            el = torch.empty(M, 8, device='cuda'); er = torch.empty(M, 8, device='cuda')
             ft64 = hh.double() @ Wd.double().t()
             el64 = (ft64.view(M, 8, 16) * al.double().view(1, 8, 16)).sum(-1)
             er64 = (ft64.view(M, 8, 16) * ar.double().view(1, 8, 16)).sum(-1)
-            assert (ft.cpu().double() - ft64).abs().max() < (2e-3 if tc else 1e-4), (M, impl)    # tc: ft stored TF32-rounded
             LOG2E = 1.4426950408889634      # scores are stored in the log2 domain (include/gnngls_b200.h)
-            assert (el.cpu().double() - LOG2E * el64).abs().max() < 2e-4 and (er.cpu().double() - LOG2E * er64).abs().max() < 2e-4
+            for ft_dtype in (_ops.FT_F32, _ops.FT_TF32, _ops.FT_F16):
+                ft = torch.empty(M, 128, device='cuda', dtype=torch.float16 if ft_dtype == _ops.FT_F16 else torch.float32)
+                el.fill_(float('nan')); er.fill_(float('nan'))
+                _lib.check(lib.gnngls_fc_forward(impl, p(hd), M, p(Wc), p(alc), p(arc), p(ft), ft_dtype, p(el), p(er),
+                                                 _ops._stream()))
+                # 10-bit-mantissa storage: |ft| <~ 8 here -> half an ulp is 2^-9 * 4
+                tol = 1e-4 if ft_dtype == _ops.FT_F32 else 5e-3
+                assert (ft.cpu().double() - ft64).abs().max() < tol, (M, impl, ft_dtype)
+                if ft_dtype == _ops.FT_TF32:
+                    assert torch.equal(ft.cpu(), models.tf32_round(ft.cpu()))
+                assert (el.cpu().double() - LOG2E * el64).abs().max() < 2e-4 and (er.cpu().double() - LOG2E * er64).abs().max() < 2e-4
             nbytes = lib.gnngls_ff_workspace_bytes(impl, M)
             ws = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
             out = torch.empty(M, 128, device='cuda')
@@ -235,3 +242,97 @@ def test_public_layer_and_gatconv_forward():
     assert got.shape == want.shape and (got - want).abs().max() < 2e-2 * want.abs().max()
     assert gat_got.shape == gat_want.shape == (G.number_of_nodes(), 8, 16)
     assert (gat_got - gat_want).abs().max() < 2e-2 * gat_want.abs().max()
+
+
+@pytest.mark.parametrize('n,B', [(3, 2), (4, 3), (5, 1), (8, 2), (9, 2), (15, 1), (16, 2), (17, 1), (24, 1), (25, 2),
+                                 (32, 1), (33, 1), (40, 1), (57, 1), (100, 1)])
+def test_aggregate_kernels_all_storage_formats(n, B):
+    """gnngls_gat_aggregate_kn / _csr with fp32, TF32 and fp16 feature storage against an fp64 evaluation of the same
+    softmax-aggregate on inputs that are exactly representable in fp16 (so only the attention weights round).
+    Sizes straddle the 8/16-member k-step and 16/32-destination tile boundaries of the tensor-core kernels."""
+    from gnngls_b200 import _lib
+    lib = _lib.load()
+    p = _ops._ptr
+    g = torch.Generator().manual_seed(100 * n + B)
+    N = n * (n - 1) // 2
+    M = B * N
+    ft = (torch.randn(M, 128, generator=g) * 2).half().float()
+    el, er = torch.randn(M, 8, generator=g) * 3, torch.randn(M, 8, generator=g) * 3       # log2-domain scores
+    h = torch.randn(M, 128, generator=g)
+    bias = torch.randn(128, generator=g) * 0.1
+    sc, sh = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1
+    # fp64 reference (dst-sorted, constant in-degree)
+    s, _ = model_port.kn_line_graph_edges(n)
+    deg = 2 * (n - 2)
+    src = torch.as_tensor(s).view(N, deg)
+    src = (src[None] + (torch.arange(B) * N)[:, None, None]).reshape(M, deg)
+    e = el.double()[src] + er.double()[:, None, :]
+    e = torch.maximum(e, 0.2 * e)
+    a = torch.softmax(e * np.log(2.0), dim=1)                                              # 2^e normalised
+    agg = torch.einsum('mdh,mdhf->mhf', a, ft.double()[src].view(M, deg, 8, 16)).reshape(M, 128)
+    ref = (h.double() + agg + bias.double()) * sc.double() + sh.double()
+    G = graph.LineGraph.complete(n, B, 'cuda')
+    indptr, indices = G.csr()
+    elc, erc, hc, bc, scc, shc = el.cuda(), er.cuda(), h.cuda(), bias.cuda(), sc.cuda(), sh.cuda()
+    nbytes = lib.gnngls_gat_kn_workspace_bytes(B, n)
+    wk = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+    scale = float(ft.abs().max())
+    for ft_dtype in (_ops.FT_F32, _ops.FT_TF32, _ops.FT_F16):
+        ftc = ft.cuda().half() if ft_dtype == _ops.FT_F16 else ft.cuda()
+        for kind in ('csr', 'kn'):
+            out = torch.full((M, 128), float('nan'), device='cuda')
+            if kind == 'csr':
+                _lib.check(lib.gnngls_gat_aggregate_csr(p(indptr), p(indices), M, p(ftc), ft_dtype, p(elc), p(erc), p(hc),
+                                                        p(bc), p(scc), p(shc), p(out), None, _ops._stream()))
+                tol = 2e-5 * scale                    # fp32 arithmetic throughout
+            else:
+                _lib.check(lib.gnngls_gat_aggregate_kn(B, n, p(ftc), ft_dtype, p(elc), p(erc), p(hc), p(bc), p(scc),
+                                                       p(shc), p(out), None, p(wk), nbytes, _ops._stream()))
+                tol = 2e-3 * scale                    # 10-bit attention weights (truncated TF32 / rounded fp16)
+            torch.cuda.synchronize()
+            err = (out.cpu().double() - ref).abs().max().item()
+            assert np.isfinite(err) and err < tol, (n, B, ft_dtype, kind, err, tol)
+
+
+def test_tf32_feature_storage_switch(monkeypatch):
+    """GNNGLS_FT_DTYPE=tf32 keeps the fp32-storage TF32 aggregate reachable from the model."""
+    port, m = make_models()
+    c = MODEL[0]
+    n, B = c.nB.tolist()
+    y16 = run(m, n, B, c.x, 'tcgen05', 'kn')
+    monkeypatch.setenv('GNNGLS_FT_DTYPE', 'tf32')
+    y32 = run(m, n, B, c.x, 'tcgen05', 'kn')
+    tol = tf32_budget(port, n, B, c.x, c.y64)
+    assert np.abs(y32 - c.y64).max() <= tol and np.abs(y16 - c.y64).max() <= tol
+
+
+def test_split_star_pipeline_matches_fused(tmp_path):
+    """GNNGLS_STAR_PIPELINE=split (star kernel + concurrently running combine kernel, read once per process, hence
+    the subprocess) computes the same merge as the default fused kernel."""
+    import os
+    import subprocess
+    import sys
+    port, m = make_models()
+    cases = [(12, 5, 4), (33, 3, 5), (100, 2, 6)]
+    script = tmp_path / 'split_run.py'
+    script.write_text(
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from tests.test_model_gpu import make_models, run\n"
+        "from gnngls_b200 import instances\n"
+        "port, m = make_models()\n"
+        "out = {}\n"
+        "for n, B, seed in %r:\n"
+        "    _, D = instances.random_instances(B, n, seed=seed)\n"
+        "    x = (instances.edge_features(D) / np.float32(np.sqrt(2))).reshape(-1, 1)\n"
+        "    out['y%%d' %% n] = run(m, n, B, x, 'tcgen05', 'kn')\n"
+        "np.savez(%r, **out)\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), cases, str(tmp_path / 'split.npz')))
+    env = dict(os.environ, GNNGLS_STAR_PIPELINE='split')
+    subprocess.run([sys.executable, str(script)], check=True, env=env, timeout=300)
+    got = np.load(tmp_path / 'split.npz')
+    for n, B, seed in cases:
+        _, D = instances.random_instances(B, n, seed=seed)
+        x = (instances.edge_features(D) / np.float32(np.sqrt(2))).reshape(-1, 1)
+        y = run(m, n, B, x, 'tcgen05', 'kn')
+        assert np.isfinite(got['y%d' % n]).all()
+        assert np.abs(got['y%d' % n] - y).max() <= 1e-5 * np.abs(y).max(), n
