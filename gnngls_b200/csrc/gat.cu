@@ -219,13 +219,15 @@ struct StarCtx {
     const float *ELs, *ERs;
     int ksteps;
     float *part;          // partial records of instance b (part + b*N*2*REC)
+    int skip_row;         // destination the tile loop must not publish (-1: none)
+    const int *NODE;      // [KP] line-graph node of {i, k} (shared memory; -1 for dead slots)
 };
 
 // publish one destination row of this warp's head: lane t of the quad holds features {2t,2t+1} and
 // {8+2t,9+2t}.  (.cg stores: the partials are consumed by another SM through L2.)
 __device__ __forceinline__ void publish_row(const StarCtx &c, int j, float2 n0, float2 n1, float den, float mx) {
-    if (j >= c.n || j == c.i) return;
-    float *rec = c.part + ((size_t)kn_node(c.i, j, c.n) * 2 + (c.i > j)) * REC;
+    if (j >= c.n || j == c.i || j == c.skip_row) return;
+    float *rec = c.part + (size_t)(c.NODE[j] * 2 + (c.i > j)) * REC;
     float *o = rec + c.hd * 16 + 2 * c.t;
     __stcg(reinterpret_cast<float2 *>(o), n0);
     __stcg(reinterpret_cast<float2 *>(o + 8), n1);
@@ -455,6 +457,8 @@ gat_kn_star_kernel(int n, const float *__restrict__ ft, const float *__restrict_
     c.Fh = Fs + warp * 16; c.ELs = ELs; c.ERs = ERs; c.ksteps = KP / 8;
     {
         c.part = part + (size_t)node0 * 2 * REC;
+        c.skip_row = -1;
+        c.NODE = NODE;
     }
     const int MT = MP / 16;
     int mt = 0;
@@ -476,7 +480,7 @@ constexpr int FH_LD = D_ + 8;   // halves; 272-byte rows: the 8 rows of an ldmat
 
 __host__ __device__ inline size_t star16_smem_bytes(int n) {
     const int KP = round_up(n, 8), KE = round_up(n, 16);
-    return (size_t)KP * FH_LD * sizeof(__half) + sizeof(float) * ((size_t)2 * KE * H_ + 3 * H_ + (size_t)KP);
+    return (size_t)KP * FH_LD * sizeof(__half) + sizeof(float) * ((size_t)4 * KE * H_ + 3 * H_ + (size_t)KP);
 }
 
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
@@ -507,14 +511,25 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], uint32_t add
 struct Star16Ctx {
     StarCtx base;          // n, i, hd, g, t, m1, m2, a1, ERs and the partial-row pointers (Fh/ELs/ksteps unused)
     const float *ELt;      // this head's el over the star, [KE] (log2 domain; dead slots -inf)
+    const float2 *EA;      // this head's (2^(el-m1), 2^(0.2(el-m1))) over the star, [KE] (dead slots 0)
     uint32_t b4_addr;      // this lane's ldmatrix.x4 row address for k-step 0
     uint32_t b2_addr;      // this lane's ldmatrix.x2 row address for the 8-member tail step
     int kfull;             // number of 16-member k-steps
     bool tail;             // an 8-member step follows (KP % 16 == 8)
 };
 
-// leaky_relu(el+er) - mx == max(el + (er-mx), 0.2*el + (0.2*er-mx)), then 2^x
-__device__ __forceinline__ float att_w(float el, float c1, float c2) { return ex2(fmaxf(el + c1, fmaf(kSlope, el, c2))); }
+// Attention weight without a per-edge exponential.  With s = el_k + er_j and mx_j the destination's maximum,
+//   2^(leaky_relu(s) - mx_j) = max(2^(s - mx_j), 2^(0.2 s - mx_j))                    (2^x is monotone)
+//                            = max(A_k * C1_j, A'_k * C2_j)
+//   A_k = 2^(el_k - m1), A'_k = 2^(0.2 (el_k - m1))                one pair per star member and head
+//   C1_j = 2^(m1 + er_j - mx_j), C2_j = 2^(0.2 (m1 + er_j) - mx_j)  one pair per destination and head
+// m1 = max_k el_k and mx_j = leaky_relu(m1 + er_j) >= the row's true maximum (any upper bound is a valid softmax
+// reference; the merge uses the published mx_j).  All four factors lie in [0, 1]: nothing overflows, and a factor
+// only underflows when the weight does.  Only the arg-max member's own row can sit far below its reference (its
+// sources exclude itself): when the runner-up m2 is more than 6 log2 units down, star16_fix_row redoes that row.
+// Cost per weight: FMUL + FMUL + FMNMX instead of FADD + FFMA + FMNMX + MUFU.EX2 -- the SFU pipe (16/clk/SM),
+// which bounded the loop, is out of it.
+__device__ __forceinline__ float att_w(float a, float a5, float c1, float c2) { return fmaxf(a * c1, a5 * c2); }
 
 template <int NT>
 __device__ __forceinline__ void star16_tiles(const Star16Ctx &c, int mt0) {
@@ -523,12 +538,14 @@ __device__ __forceinline__ void star16_tiles(const Star16Ctx &c, int mt0) {
     float acc0[NT][4], acc1[NT][4], accs[NT][4];
 #pragma unroll
     for (int u = 0; u < NT; ++u) {
-        const int j_lo = (mt0 + u) * 16 + b.g, j_hi = j_lo + 8;
-        const float er_lo = b.ERs[j_lo * H_ + b.hd], er_hi = b.ERs[j_hi * H_ + b.hd];
-        mxa[u][0] = lrelu(((b.a1 == j_lo) ? b.m2 : b.m1) + er_lo);
-        mxa[u][1] = lrelu(((b.a1 == j_hi) ? b.m2 : b.m1) + er_hi);
-        c1a[u][0] = er_lo - mxa[u][0]; c2a[u][0] = kSlope * er_lo - mxa[u][0];
-        c1a[u][1] = er_hi - mxa[u][1]; c2a[u][1] = kSlope * er_hi - mxa[u][1];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int j = (mt0 + u) * 16 + b.g + 8 * r;
+            const float s = b.m1 + b.ERs[j * H_ + b.hd];
+            mxa[u][r] = lrelu(s);
+            c1a[u][r] = ex2(s - mxa[u][r]);
+            c2a[u][r] = ex2(kSlope * s - mxa[u][r]);
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) { acc0[u][q] = 0.f; acc1[u][q] = 0.f; accs[u][q] = 0.f; }
     }
@@ -536,16 +553,16 @@ __device__ __forceinline__ void star16_tiles(const Star16Ctx &c, int mt0) {
     auto kstep16 = [&](int ks, auto diag_tag) {
         constexpr bool DIAG = decltype(diag_tag)::value;
         const int ka = ks * 16 + 2 * b.t, kb = ka + 8;
-        const float2 ea = *reinterpret_cast<const float2 *>(c.ELt + ka);
-        const float2 eb = *reinterpret_cast<const float2 *>(c.ELt + kb);
+        const float4 pa = *reinterpret_cast<const float4 *>(c.EA + ka);      // (A, A') of members ka, ka+1
+        const float4 pb = *reinterpret_cast<const float4 *>(c.EA + kb);      //          ... of members kb, kb+1
         uint32_t B[4];
         ldmatrix_x4_trans(B, c.b4_addr + (uint32_t)ks * (16 * FH_LD * 2));
 #pragma unroll
         for (int u = 0; u < NT; ++u) {
-            float w00 = att_w(ea.x, c1a[u][0], c2a[u][0]), w01 = att_w(ea.y, c1a[u][0], c2a[u][0]);   // row lo, k = ka, ka+1
-            float w10 = att_w(ea.x, c1a[u][1], c2a[u][1]), w11 = att_w(ea.y, c1a[u][1], c2a[u][1]);   // row hi
-            float w20 = att_w(eb.x, c1a[u][0], c2a[u][0]), w21 = att_w(eb.y, c1a[u][0], c2a[u][0]);   // row lo, k = kb, kb+1
-            float w30 = att_w(eb.x, c1a[u][1], c2a[u][1]), w31 = att_w(eb.y, c1a[u][1], c2a[u][1]);   // row hi
+            float w00 = att_w(pa.x, pa.y, c1a[u][0], c2a[u][0]), w01 = att_w(pa.z, pa.w, c1a[u][0], c2a[u][0]);   // row lo, k = ka, ka+1
+            float w10 = att_w(pa.x, pa.y, c1a[u][1], c2a[u][1]), w11 = att_w(pa.z, pa.w, c1a[u][1], c2a[u][1]);   // row hi
+            float w20 = att_w(pb.x, pb.y, c1a[u][0], c2a[u][0]), w21 = att_w(pb.z, pb.w, c1a[u][0], c2a[u][0]);   // row lo, k = kb, kb+1
+            float w30 = att_w(pb.x, pb.y, c1a[u][1], c2a[u][1]), w31 = att_w(pb.z, pb.w, c1a[u][1], c2a[u][1]);   // row hi
             if (DIAG) {                                   // a node is not its own neighbour
                 const int j_lo = (mt0 + u) * 16 + b.g, j_hi = j_lo + 8;
                 if (ka == j_lo) w00 = 0.f;
@@ -570,14 +587,14 @@ __device__ __forceinline__ void star16_tiles(const Star16Ctx &c, int mt0) {
     for (int ks = d1; ks < c.kfull; ++ks) kstep16(ks, std::false_type{});
     if (c.tail) {
         const int ka = c.kfull * 16 + 2 * b.t;
-        const float2 ea = *reinterpret_cast<const float2 *>(c.ELt + ka);
+        const float4 pa = *reinterpret_cast<const float4 *>(c.EA + ka);
         uint32_t B[2];
         ldmatrix_x2_trans(B, c.b2_addr);
 #pragma unroll
         for (int u = 0; u < NT; ++u) {
             const int j_lo = (mt0 + u) * 16 + b.g, j_hi = j_lo + 8;
-            float w00 = att_w(ea.x, c1a[u][0], c2a[u][0]), w01 = att_w(ea.y, c1a[u][0], c2a[u][0]);
-            float w10 = att_w(ea.x, c1a[u][1], c2a[u][1]), w11 = att_w(ea.y, c1a[u][1], c2a[u][1]);
+            float w00 = att_w(pa.x, pa.y, c1a[u][0], c2a[u][0]), w01 = att_w(pa.z, pa.w, c1a[u][0], c2a[u][0]);
+            float w10 = att_w(pa.x, pa.y, c1a[u][1], c2a[u][1]), w11 = att_w(pa.z, pa.w, c1a[u][1], c2a[u][1]);
             if (ka == j_lo) w00 = 0.f;
             if (ka + 1 == j_lo) w01 = 0.f;
             if (ka == j_hi) w10 = 0.f;
@@ -596,6 +613,47 @@ __device__ __forceinline__ void star16_tiles(const Star16Ctx &c, int mt0) {
     }
 }
 
+// The destination that is itself the head's arg-max star member, when the other members are far below it: its
+// weights relative to m1 would be < 2^-6 and lose fp16 precision (or flush to zero).  One row per head and star:
+// the warp evaluates it directly in fp32 against m2 -- lanes over members, shuffle reduction -- and publishes it.
+__device__ __forceinline__ void star16_fix_row(const Star16Ctx &c, const __half *Fh, int KP, int lane) {
+    const StarCtx &b = c.base;
+    const int j = b.a1;
+    if (j < 0 || j >= b.n || j == b.i) return;            // (cannot happen: the arg-max is a live member)
+    const float erj = b.ERs[j * H_ + b.hd];
+    const float mx = lrelu(b.m2 + erj);
+    float num[16], den = 0.f;
+#pragma unroll
+    for (int f = 0; f < 16; ++f) num[f] = 0.f;
+    for (int k = lane; k < KP; k += 32) {
+        const float w = (k == j) ? 0.f : ex2(lrelu(c.ELt[k] + erj) - mx);     // dead slots: el = -inf -> 0
+        const uint4 r0 = *reinterpret_cast<const uint4 *>(Fh + (size_t)k * FH_LD + b.hd * 16);
+        const uint4 r1 = *reinterpret_cast<const uint4 *>(Fh + (size_t)k * FH_LD + b.hd * 16 + 8);
+        const uint32_t raw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float2 v = __half22float2(*reinterpret_cast<const __half2 *>(&raw[q]));
+            num[2 * q] = fmaf(w, v.x, num[2 * q]);
+            num[2 * q + 1] = fmaf(w, v.y, num[2 * q + 1]);
+        }
+        den += w;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        den += __shfl_xor_sync(0xffffffffu, den, off);
+#pragma unroll
+        for (int f = 0; f < 16; ++f) num[f] += __shfl_xor_sync(0xffffffffu, num[f], off);
+    }
+    if (lane == 0) {
+        float *rec = b.part + ((size_t)kn_node(b.i, j, b.n) * 2 + (b.i > j)) * REC;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            __stcg(reinterpret_cast<float4 *>(rec + b.hd * 16 + 4 * q), make_float4(num[4 * q], num[4 * q + 1], num[4 * q + 2], num[4 * q + 3]));
+        __stcg(rec + D_ + b.hd, den);
+        __stcg(rec + D_ + H_ + b.hd, mx);
+    }
+}
+
 template <bool FUSED>
 __device__ __forceinline__ void star_f16_body(int n, const __half *__restrict__ ft, const float *__restrict__ el, const float *__restrict__ er,
                        float *__restrict__ part,
@@ -608,7 +666,8 @@ __device__ __forceinline__ void star_f16_body(int n, const __half *__restrict__ 
     __half *Fh = reinterpret_cast<__half *>(smem_raw);                        // [KP][FH_LD] fp16 ft rows of the star
     float *ELt = reinterpret_cast<float *>(Fh + (size_t)KP * FH_LD);          // [8][KE] el, head-major (dead slots: -inf)
     float *ERs = ELt + (size_t)H_ * KE;                                       // [KE][8] er (dead slots: 0)
-    float *TM1 = ERs + (size_t)KE * H_;
+    float2 *EA = reinterpret_cast<float2 *>(ERs + (size_t)KE * H_);           // [8][KE] (2^(el-m1), 2^(0.2(el-m1))), head-major
+    float *TM1 = reinterpret_cast<float *>(EA + (size_t)H_ * KE);
     float *TM2 = TM1 + H_;
     int *TA1 = reinterpret_cast<int *>(TM2 + H_);
     int *NODE = TA1 + H_;                                                     // [KP]
@@ -667,7 +726,18 @@ __device__ __forceinline__ void star_f16_body(int n, const __half *__restrict__ 
         c.base.m1 = t2.m1; c.base.m2 = t2.m2; c.base.a1 = t2.a1;
         c.base.Fh = nullptr; c.base.ELs = nullptr; c.base.ERs = ERs; c.base.ksteps = 0;
         c.base.part = part + (size_t)node0 * 2 * REC;
+        // the arg-max member's own row: fine in the shared factorisation unless the runner-up is far below
+        // (its weights would sink towards fp16 subnormals); then it is redone exactly
+        const bool fix = t2.m1 - t2.m2 > 6.f;
+        c.base.skip_row = fix ? t2.a1 : -1;
+        c.base.NODE = NODE;
         c.ELt = ELt + warp * KE;
+        c.EA = EA + warp * KE;
+        for (int k = lane; k < KE; k += 32) {                                 // per-member factors of this warp's head
+            const float d = ELt[warp * KE + k] - t2.m1;
+            EA[warp * KE + k] = make_float2(ex2(d), ex2(kSlope * d));
+        }
+        __syncwarp();
         const uint32_t fh = (uint32_t)__cvta_generic_to_shared(Fh);
         const int q = lane >> 3, r = lane & 7;
         c.b4_addr = fh + (uint32_t)(((r + 8 * (q & 1)) * FH_LD + warp * 16 + 8 * (q >> 1)) * 2);
@@ -678,6 +748,7 @@ __device__ __forceinline__ void star_f16_body(int n, const __half *__restrict__ 
         int mt = 0;
         for (; mt + 2 <= MT; mt += 2) star16_tiles<2>(c, mt);
         if (mt < MT) star16_tiles<1>(c, mt);
+        if (fix) star16_fix_row(c, Fh, KP, lane);
     }
     if (FUSED) {
         star_finish<3>(n, i, b, node0, reinterpret_cast<int *>(ELt), part, arrive, h, bias, bn_scale, bn_shift, h1, h1_tf32);

@@ -258,6 +258,11 @@ def test_aggregate_kernels_all_storage_formats(n, B):
     M = B * N
     ft = (torch.randn(M, 128, generator=g) * 2).half().float()
     el, er = torch.randn(M, 8, generator=g) * 3, torch.randn(M, 8, generator=g) * 3       # log2-domain scores
+    # a few dominant sources (far above every other member of their stars): the fp16 star kernel then takes its
+    # exact-row path for the destination that is itself the arg-max member
+    hot = torch.randint(0, M, (max(1, M // 7),), generator=g)
+    el[hot, torch.randint(0, 8, (len(hot),), generator=g)] += 25.0
+    el[hot[0]] += 60.0
     h = torch.randn(M, 128, generator=g)
     bias = torch.randn(128, generator=g) * 0.1
     sc, sh = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1

@@ -10,9 +10,11 @@ __global__ void __launch_bounds__(STAR_THREADS, MINB) loop_kernel(int n, int rep
     __half *Fh = reinterpret_cast<__half *>(smem_raw);
     float *ELt = reinterpret_cast<float *>(Fh + (size_t)KP * FH_LD);
     float *ERs = ELt + (size_t)H_ * KE;
+    float2 *EA = reinterpret_cast<float2 *>(ERs + (size_t)KE * H_);
     for (int i = threadIdx.x; i < KP * FH_LD; i += STAR_THREADS) Fh[i] = __float2half((float)((i * 31) % 17) * 0.1f - 0.8f);
     for (int i = threadIdx.x; i < H_ * KE; i += STAR_THREADS) ELt[i] = (i % KE) < n ? (float)((i * 13) % 23) * 0.2f - 2.f : -INFINITY;
     for (int i = threadIdx.x; i < KE * H_; i += STAR_THREADS) ERs[i] = (float)((i * 7) % 19) * 0.2f - 2.f;
+    for (int i = threadIdx.x; i < H_ * KE; i += STAR_THREADS) EA[i] = make_float2(exp2f(ELt[i] - 2.4f), exp2f(0.2f * (ELt[i] - 2.4f)));
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Star16Ctx c;
@@ -21,6 +23,8 @@ __global__ void __launch_bounds__(STAR_THREADS, MINB) loop_kernel(int n, int rep
     c.base.Fh = nullptr; c.base.ELs = nullptr; c.base.ERs = ERs; c.base.ksteps = 0;
     c.base.part = part + (size_t)blockIdx.x * n * (n - 1) * REC;
     c.ELt = ELt + warp * KE;
+    c.EA = EA + warp * KE;
+    c.base.skip_row = 5;
     const uint32_t fh = (uint32_t)__cvta_generic_to_shared(Fh);
     const int q = lane >> 3, r = lane & 7;
     c.b4_addr = fh + (uint32_t)(((r + 8 * (q & 1)) * FH_LD + warp * 16 + 8 * (q >> 1)) * 2);
