@@ -309,16 +309,17 @@ def main():
         tp = os.path.join(ROOT, 'profiles', 'gat_kn_star_traffic.json')      # from the committed ncu --set full capture
         if os.path.exists(tp):
             traffic = json.load(open(tp))['dram_bytes_per_instance_layer'] * per_call_instances
-        roof = {'kernel': 'gat_kn_star_kernel (K_n edge-softmax/aggregate + skip + BN1, one launch per layer and micro-batch)',
+        roof = {'kernel': 'gat_kn_star_f16_fused_kernel (K_n edge-softmax/aggregate + skip + BN1, one launch per layer and micro-batch)',
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes_per_instance_layer * per_call_instances,
                 'avg_launch_ms': gat_ms / gat_calls, 'launches_timed': gat_calls,
-                'compulsory_hbm_gbs': (N_nodes * (2 * 512 + 2 * 64 + 512 + 2 * 512) * S * 8 * args.steps) / (gat_ms / 1e3) / 1e9,
+                'compulsory_hbm_gbs': (N_nodes * (256 + 2 * 32 + 512 + 512) * S * 8 * args.steps) / (gat_ms / 1e3) / 1e9,
                 'note': 'achieved = ALGORITHMIC gather bytes of SURVEY 8(d) (544 B/edge + 544 B/node) / kernel time. The '
                         'star kernel stages each ft row in shared memory once per incident vertex (2 reads per row) and '
                         'serves the 2(n-2)=196-fold logical re-reads from SMEM/registers, so frac > 1 measures reuse, not '
-                        'skipped work; `traffic` is the real DRAM traffic per launch from ncu (DESIGN.md section 5).'}
+                        'skipped work; `traffic` is the real DRAM traffic per launch from ncu (DESIGN.md section 5); compulsory_hbm_gbs '
+                        'counts each node once: fp16 ft 256 B + el/er 64 B + skip h 512 B + h1 512 B.'}
     total_stage = sum(v[0] for v in stages.values())
     stage_ms = {k: round(v[0] / args.steps, 3) for k, v in stages.items()}
     cand_2opt, cand_rel = (n - 2) * (n - 3) // 2, (n - 2) ** 2

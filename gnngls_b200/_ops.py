@@ -9,7 +9,7 @@ from . import _lib
 
 OP_TWO_OPT, OP_RELOCATE = 0, 1
 GUIDE_MATRIX_F64, GUIDE_EDGEVEC_F32 = 0, 1
-DENSE_TCGEN05, DENSE_SIMT = 0, 1
+DENSE_TCGEN05, DENSE_SIMT, DENSE_TCGEN05_F16 = 0, 1, 2
 FT_F32, FT_TF32, FT_F16 = 0, 1, 2       # gnngls_ft_dtype
 INST_EVENTS_TRUNCATED, INST_PENALTY_OVERFLOW, INST_STALLED = 1, 2, 4
 

@@ -507,6 +507,22 @@ int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, 
     return GNNGLS_OK;
 }
 
+// row-major fp16 [rows, cols] -> box [box_rows rows, 64 cols] (128 bytes), 128B swizzle
+int make_map_f16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    GNNGLS_REQUIRE(fn, GNNGLS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    GNNGLS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, GNNGLS_ERR_BAD_ARG, "TMA operand not 16-byte aligned");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GNNGLS_REQUIRE(r == CUDA_SUCCESS, GNNGLS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return GNNGLS_OK;
+}
+
 template <int N_TOTAL, int K_TOTAL, int EPI>
 int launch_tc_gemm(const float *A, const float *W, const EpiParams &p, cudaStream_t st) {
     CUtensorMap tmA, tmB;
@@ -555,6 +571,28 @@ constexpr int FF_TMEM_COLS = 512;
 constexpr size_t FF_SMEM = 1024 + FF_A_BYTES + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES + 4 * STG_TILE_BYTES + FF_SVEC * 4 +
                            FF_NBARS * 8 + 16;
 
+// kind::f16 instruction descriptor: F32 accumulate, A/B = F16 (format 0), K-major A and B
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::f16: K = 16 per instruction, A: lane = row, one 32-bit column per PAIR of k
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t *v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32 (A: lane = row, one fp32 column per k)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -582,11 +620,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float *v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int CL>      // CTAs per cluster sharing (multicasting) the streamed weights: 1, 2 or 4
+// F16: weights arrive as fp16, both TMEM operands are packed fp16 pairs and the contractions run as kind::f16
+// (K = 16 per instruction: half the MMAs and half the streamed weight bytes; fp16 carries the same 10-bit
+// mantissa as the TF32 operands of the other variant, values saturate at +-65504).
+template <int CL, bool F16>      // CL: CTAs per cluster sharing (multicasting) the streamed weights: 1, 2 or 4
 __global__ void __launch_bounds__(FF_THREADS, 1)
-ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
+ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const EpiParams p, const float *__restrict__ b1,
                      const int round_a) {
+    static_assert(!F16 || CL == 1, "the fp16 variant does not multicast");
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024B-aligned, still .shared
     unsigned char *sA = smem;
@@ -674,7 +716,14 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     if (round_a) x = tf32_rna4(x);            // operand is the raw fp32 activation: round here, not truncate in the MMA
                     v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
                 }
-                tmem_st_32x32(tm_a + lane_sel + kb * BK, v);
+                if (F16) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
+                    tmem_st_32x16(tm_a + lane_sel + kb * (BK / 2), pk);
+                } else {
+                    tmem_st_32x32(tm_a + lane_sel + kb * BK, v);
+                }
             }
             tmem_st_wait();
             tc_fence_before();
@@ -712,17 +761,40 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 else tma_load_2d_mc(&tmW2, &w_full[stage], dst + (int)crank * BR * 128, c * FF_HC + half * BK, (int)crank * BR, kMask);
                 if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
             };
+            // fp16: one stage holds a whole chunk of W1 (2 boxes [64 units x 64 k]) or of W2 (1 box [128 outputs x 64 units])
+            auto load_w1_f16 = [&](int c) {
+                mbar_wait(&w_empty[stage], phase ^ 1);
+                unsigned char *dst = sW + (size_t)stage * FF_WSTAGE_BYTES;
+                mbar_expect_tx(&w_full[stage], FF_WSTAGE_BYTES);
+                for (int kk = 0; kk < 2; ++kk) tma_load_2d(&tmW1, &w_full[stage], dst + kk * (FF_HC * 128), kk * 64, c * FF_HC);
+                if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+            };
+            auto load_w2_f16 = [&](int c) {
+                mbar_wait(&w_empty[stage], phase ^ 1);
+                mbar_expect_tx(&w_full[stage], FF_WSTAGE_BYTES);
+                tma_load_2d(&tmW2, &w_full[stage], sW + (size_t)stage * FF_WSTAGE_BYTES, c * FF_HC, 0);
+                if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+            };
             for (int64_t w = tile0; w < m_tiles; w += tile_step) {
-                for (int c = 0; c < FF_CHUNKS; ++c) {
-                    load_w1(c, 0); load_w1(c, 1);
-                    if (c >= 1) { load_w2(c - 1, 0); load_w2(c - 1, 1); }
+                if (F16) {
+                    for (int c = 0; c < FF_CHUNKS; ++c) {
+                        load_w1_f16(c);
+                        if (c >= 1) load_w2_f16(c - 1);
+                    }
+                    load_w2_f16(FF_CHUNKS - 1);
+                } else {
+                    for (int c = 0; c < FF_CHUNKS; ++c) {
+                        load_w1(c, 0); load_w1(c, 1);
+                        if (c >= 1) { load_w2(c - 1, 0); load_w2(c - 1, 1); }
+                    }
+                    load_w2(FF_CHUNKS - 1, 0); load_w2(FF_CHUNKS - 1, 1);
                 }
-                load_w2(FF_CHUNKS - 1, 0); load_w2(FF_CHUNKS - 1, 1);
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (warp-uniform control flow)
-        constexpr uint32_t idesc1 = make_idesc_tf32(BM, FF_HC), idesc2 = make_idesc_tf32(BM, BN);
+        constexpr uint32_t idesc1 = F16 ? make_idesc_f16(BM, FF_HC) : make_idesc_tf32(BM, FF_HC);
+        constexpr uint32_t idesc2 = F16 ? make_idesc_f16(BM, BN) : make_idesc_tf32(BM, BN);
         uint32_t stage = 0, phase = 0, it = 0;
         uint32_t n_h[2] = {0, 0};
         for (int64_t w = tile0; w < m_tiles; w += tile_step, ++it) {
@@ -731,24 +803,57 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             auto gemm2 = [&](int c) {
                 const int g = c & 1;
                 mbar_wait(&h_full[g], n_h[g] & 1); ++n_h[g];  // epilogue-1 has rewritten DH[g] with the hidden chunk
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
+                if (F16) {
                     mbar_wait(&w_full[stage], phase);
                     tc_fence_after();
                     const uint64_t db = make_sw128_kmajor_desc(smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES));
                     if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / 8; ++k)
-                            umma_tf32_ts(tm_acc, tm_dh + g * FF_HC + half * BK + 8 * k, db + (uint64_t)(2 * k), idesc2, (c | half | k) != 0);
-                        if (CL == 1) umma_commit(&w_empty[stage]); else umma_commit_mc(&w_empty[stage], kMask);
+                        for (int k = 0; k < FF_HC / 16; ++k)     // hidden units [16k, 16k+16): packed by the epilogue warp hf = k>>1 at columns 32*hf + 8*(k&1)
+                            umma_f16_ts(tm_acc, tm_dh + g * FF_HC + (k >> 1) * 32 + (k & 1) * 8, db + (uint64_t)(2 * k), idesc2, (c | k) != 0);
+                        umma_commit(&w_empty[stage]);
                     }
                     __syncwarp();
                     if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                } else {
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        mbar_wait(&w_full[stage], phase);
+                        tc_fence_after();
+                        const uint64_t db = make_sw128_kmajor_desc(smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES));
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < BK / 8; ++k)
+                                umma_tf32_ts(tm_acc, tm_dh + g * FF_HC + half * BK + 8 * k, db + (uint64_t)(2 * k), idesc2, (c | half | k) != 0);
+                            if (CL == 1) umma_commit(&w_empty[stage]); else umma_commit_mc(&w_empty[stage], kMask);
+                        }
+                        __syncwarp();
+                        if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                    }
                 }
             };
             mbar_wait(at_full, it & 1);                       // A tile is in TMEM
             for (int c = 0; c < FF_CHUNKS; ++c) {
                 const int g = c & 1;
+                if (F16) {
+                    mbar_wait(&w_full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sw = smem_u32(sW + (size_t)stage * FF_WSTAGE_BYTES);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint64_t db = make_sw128_kmajor_desc(sw + kk * (FF_HC * 128));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)       // k range [64kk + 16k, +16) = packed columns 32kk + 8k
+                                umma_f16_ts(tm_dh + g * FF_HC, tm_a + kk * 32 + 8 * k, db + (uint64_t)(2 * k), idesc1, (kk | k) != 0);
+                        }
+                        umma_commit(&w_empty[stage]);
+                        umma_commit(&d1_full[g]);
+                        if (c == FF_CHUNKS - 1) umma_commit(at_empty);   // last reader of A[tmem]
+                    }
+                    __syncwarp();
+                    if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                } else {
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     mbar_wait(&w_full[stage], phase);
@@ -771,6 +876,7 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     }
                     __syncwarp();
                     if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                }
                 }
                 if (c == 1) { mbar_wait(&d2_empty[d], ((it >> 1) & 1) ^ 1); tc_fence_after(); }   // final epilogue two tiles back drained D2[d]
                 if (c >= 1) gemm2(c - 1);
@@ -798,10 +904,21 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 b = *reinterpret_cast<const float4 *>(bb + 4 * j);
-                    v[4 * j] = tf32_rna(fmaxf(v[4 * j] + b.x, 0.f)); v[4 * j + 1] = tf32_rna(fmaxf(v[4 * j + 1] + b.y, 0.f));
-                    v[4 * j + 2] = tf32_rna(fmaxf(v[4 * j + 2] + b.z, 0.f)); v[4 * j + 3] = tf32_rna(fmaxf(v[4 * j + 3] + b.w, 0.f));
+                    v[4 * j] = fmaxf(v[4 * j] + b.x, 0.f); v[4 * j + 1] = fmaxf(v[4 * j + 1] + b.y, 0.f);
+                    v[4 * j + 2] = fmaxf(v[4 * j + 2] + b.z, 0.f); v[4 * j + 3] = fmaxf(v[4 * j + 3] + b.w, 0.f);
+                    if (!F16) {                               // (the fp16 variant rounds when it packs)
+                        v[4 * j] = tf32_rna(v[4 * j]); v[4 * j + 1] = tf32_rna(v[4 * j + 1]);
+                        v[4 * j + 2] = tf32_rna(v[4 * j + 2]); v[4 * j + 3] = tf32_rna(v[4 * j + 3]);
+                    }
                 }
-                tmem_st_32x32(ta, v);                         // in place: D1 -> H
+                if (F16) {                                    // relu output, packed: 16 columns at 32*hf (never the columns the
+                    uint32_t pk[16];                          // other half's warp is still reading)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
+                    tmem_st_32x16(ta, pk);
+                } else {
+                    tmem_st_32x32(ta, v);                     // in place: D1 -> H
+                }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -818,14 +935,19 @@ ff_fused_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 }
 
-template <int CL>
-int launch_ff_fused_cl(const float *a_op, int round_a, const float *W1, const float *b1, const float *W2, const EpiParams &p,
+template <int CL, bool F16>
+int launch_ff_fused_cl(const float *a_op, int round_a, const void *W1, const float *b1, const void *W2, const EpiParams &p,
                        cudaStream_t st) {
     CUtensorMap tmA, tmW1, tmW2;
     if (int rc = make_map(&tmA, a_op, (uint64_t)p.M, D_, BM)) return rc;
-    if (int rc = make_map(&tmW1, W1, HID_, D_, CL == 1 ? FF_HC : 128 / CL)) return rc;     // box [rows x 32 k]
-    if (int rc = make_map(&tmW2, W2, D_, HID_, CL == 1 ? BM : 128 / CL)) return rc;
-    auto kern = ff_fused_tf32_kernel<CL>;
+    if (F16) {
+        if (int rc = make_map_f16(&tmW1, W1, HID_, D_, FF_HC)) return rc;                   // box [64 units x 64 k]
+        if (int rc = make_map_f16(&tmW2, W2, D_, HID_, BM)) return rc;                      // box [128 outputs x 64 units]
+    } else {
+        if (int rc = make_map(&tmW1, static_cast<const float *>(W1), HID_, D_, CL == 1 ? FF_HC : 128 / CL)) return rc;     // box [rows x 32 k]
+        if (int rc = make_map(&tmW2, static_cast<const float *>(W2), D_, HID_, CL == 1 ? BM : 128 / CL)) return rc;
+    }
+    auto kern = ff_fused_kernel<CL, F16>;
     GNNGLS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
     const int64_t tiles = (p.M + BM - 1) / BM;
     const int sms = gnngls::device_sm_count();
@@ -843,21 +965,22 @@ int launch_ff_fused_cl(const float *a_op, int round_a, const float *W1, const fl
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     GNNGLS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmW1, tmW2, p, b1, round_a));
-    GNNGLS_LAUNCH_OK("ff_fused_tf32_kernel");
+    GNNGLS_LAUNCH_OK("ff_fused_kernel");
     return GNNGLS_OK;
 }
 
-int launch_ff_fused(const float *a_op, int round_a, const float *W1, const float *b1, const float *W2, const EpiParams &p,
-                    cudaStream_t st) {
+int launch_ff_fused(const float *a_op, int round_a, const void *W1, const float *b1, const void *W2, const EpiParams &p,
+                    cudaStream_t st, bool f16) {
+    if (f16) return launch_ff_fused_cl<1, true>(a_op, round_a, W1, b1, W2, p, st);
     static int cl = -1;                                       // GNNGLS_FF_CLUSTER = 1 | 2 | 4 (default 1)
     if (cl < 0) {
         const char *e = getenv("GNNGLS_FF_CLUSTER");
         cl = e ? atoi(e) : 1;      // multicast measured neutral at 2, slower at 4 (profiles/r1_ff_cluster.md): default off
         if (cl != 1 && cl != 2 && cl != 4) cl = 1;
     }
-    if (cl == 1) return launch_ff_fused_cl<1>(a_op, round_a, W1, b1, W2, p, st);
-    if (cl == 4) return launch_ff_fused_cl<4>(a_op, round_a, W1, b1, W2, p, st);
-    return launch_ff_fused_cl<2>(a_op, round_a, W1, b1, W2, p, st);
+    if (cl == 1) return launch_ff_fused_cl<1, false>(a_op, round_a, W1, b1, W2, p, st);
+    if (cl == 4) return launch_ff_fused_cl<4, false>(a_op, round_a, W1, b1, W2, p, st);
+    return launch_ff_fused_cl<2, false>(a_op, round_a, W1, b1, W2, p, st);
 }
 
 // ================================================================================================
@@ -994,12 +1117,12 @@ extern "C" int gnngls_fc_forward(int impl, const float *h, int64_t M, const floa
 }
 
 extern "C" size_t gnngls_ff_workspace_bytes(int impl, int64_t M) {
-    if (impl == GNNGLS_DENSE_TCGEN05) return 0;               // fused: the hidden activations stay on chip
+    if (impl == GNNGLS_DENSE_TCGEN05 || impl == GNNGLS_DENSE_TCGEN05_F16) return 0;   // fused: the hidden activations stay on chip
     return M > 0 ? (size_t)M * HID_ * sizeof(float) : 0;     // debug path materialises hidden [M,512]
 }
 
-extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32, int64_t M, const float *W1,
-                                 const float *b1, const float *W2, const float *b2, const float *bn_scale,
+extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32, int64_t M, const void *W1,
+                                 const float *b1, const void *W2, const float *b2, const float *bn_scale,
                                  const float *bn_shift, float *h_out, float *h_out_tf32, void *workspace,
                                  size_t workspace_bytes, void *stream) {
     GNNGLS_REQUIRE(h1 && W1 && b1 && W2 && b2 && bn_scale && bn_shift && h_out, GNNGLS_ERR_BAD_ARG, "null pointer argument");
@@ -1015,10 +1138,12 @@ extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32
     p2.M = M; p2.out = h_out; p2.out_tf32 = h_out_tf32; p2.v0 = b2; p2.v1 = bn_scale; p2.v2 = bn_shift; p2.skip = h1;
     const float *a1 = h1_tf32 ? h1_tf32 : h1;                 // GEMM operand; the skip path always reads fp32 h1
     if (impl == GNNGLS_DENSE_TCGEN05)
-        return launch_ff_fused(a1, h1_tf32 == nullptr, W1, b1, W2, p2, st);      // no pre-rounded copy: round while staging
+        return launch_ff_fused(a1, h1_tf32 == nullptr, W1, b1, W2, p2, st, false);   // no pre-rounded copy: round while staging
+    if (impl == GNNGLS_DENSE_TCGEN05_F16)
+        return launch_ff_fused(h1, 0, W1, b1, W2, p2, st, true);                     // fp16 weights; h1 is packed to fp16 while staging
     if (impl == GNNGLS_DENSE_SIMT) {
-        if (int rc = launch_simt_gemm<HID_, D_, EPI_FF1>(a1, W1, p1, st)) return rc;
-        return launch_simt_gemm<D_, HID_, EPI_FF2>(hid, W2, p2, st);
+        if (int rc = launch_simt_gemm<HID_, D_, EPI_FF1>(a1, static_cast<const float *>(W1), p1, st)) return rc;
+        return launch_simt_gemm<D_, HID_, EPI_FF2>(hid, static_cast<const float *>(W2), p2, st);
     }
     GNNGLS_REQUIRE(false, GNNGLS_ERR_BAD_ARG, "unknown dense impl %d", impl);
 }

@@ -175,6 +175,8 @@ class AttentionLayer(nn.Module):
                  W1=f(ff[0].weight), b1=f(ff[0].bias), W2=f(ff[2].weight), b2=f(ff[2].bias), s2=s2, t2=t2)
         for k in ('Wfc', 'W1', 'W2'):
             d[k + '_tf32'] = tf32_round(d[k])
+        for k in ('W1', 'W2'):                              # fp16 feed-forward variant (same 10-bit mantissa as TF32)
+            d[k + '_f16'] = d[k].clamp(-65504.0, 65504.0).to(torch.float16).contiguous()
         return d
 
     def forward(self, G, x, _params=None, _ws=None, _dense_impl=None, _gat_impl='auto', _out=None, _x_tf32=None,
@@ -202,9 +204,13 @@ class AttentionLayer(nn.Module):
         wk = _buf(ws, 'ff_ws', (nbytes,), torch.uint8, dev)
         out = _out if _out is not None else torch.empty(M, 128, dtype=torch.float32, device=dev)
         p = _ops._ptr
+        # tensor-core path: the feed-forward runs as kind::f16 unless GNNGLS_FF_DTYPE=tf32
+        ff_impl, wsfx = impl, sfx
+        if tc and os.environ.get('GNNGLS_FF_DTYPE', 'f16').lower() != 'tf32':
+            ff_impl, wsfx = _ops.DENSE_TCGEN05_F16, '_f16'
         with stage('ff'):
-            _lib.check(lib.gnngls_ff_forward(impl, p(h1), p(h1r), M, p(prm['W1' + sfx]), p(prm['b1']),
-                                             p(prm['W2' + sfx]), p(prm['b2']), p(prm['s2']), p(prm['t2']), p(out),
+            _lib.check(lib.gnngls_ff_forward(ff_impl, p(h1), p(h1r), M, p(prm['W1' + wsfx]), p(prm['b1']),
+                                             p(prm['W2' + wsfx]), p(prm['b2']), p(prm['s2']), p(prm['t2']), p(out),
                                              p(_out_tf32), p(wk), nbytes, _ops._stream()))
         return out
 

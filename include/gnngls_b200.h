@@ -150,7 +150,8 @@ int gnngls_embed_forward(const float *x, int64_t M, int in_dim, const float *W, 
 /* dense implementation selector for the fc / feed-forward contractions */
 typedef enum gnngls_dense_impl {
     GNNGLS_DENSE_TCGEN05 = 0,   /* TMA-fed tcgen05.mma kind::tf32, accumulators in TMEM (default) */
-    GNNGLS_DENSE_SIMT = 1       /* plain fp32 CUDA-core kernel: debug cross-check only            */
+    GNNGLS_DENSE_SIMT = 1,      /* plain fp32 CUDA-core kernel: debug cross-check only            */
+    GNNGLS_DENSE_TCGEN05_F16 = 2 /* feed-forward only: tcgen05.mma kind::f16, W1/W2 passed as fp16 */
 } gnngls_dense_impl;
 
 /* storage format of the projected features ft[M,128] handed from fc to the aggregates */
@@ -198,10 +199,13 @@ int gnngls_gat_aggregate_kn(int B, int n, const void *ft, int ft_dtype, const fl
  *   h_out = BN2(h1 + W2 * relu(W1 * h1 + b1) + b2),  W1[512,128], W2[128,512]
  * h1_tf32 (nullable) is a pre-rounded operand copy for the first contraction; when NULL the tensor-core
  * kernel rounds h1 to TF32 itself while staging the tile into tensor memory.  The skip always reads h1.
+ * GNNGLS_DENSE_TCGEN05_F16: W1/W2 are IEEE fp16 (same row-major shapes), h1 is packed to fp16 while it is staged
+ * into tensor memory (h1_tf32 is ignored) and the hidden activations are kept as fp16 pairs: same 10-bit
+ * mantissa as the TF32 variant, half the MMAs and half the streamed weight bytes; values saturate at +-65504.
  * `workspace` must hold gnngls_ff_workspace_bytes(impl, M) bytes (may be 0). */
 size_t gnngls_ff_workspace_bytes(int impl, int64_t M);
-int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32, int64_t M, const float *W1,
-                      const float *b1, const float *W2, const float *b2, const float *bn_scale,
+int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32, int64_t M, const void *W1,
+                      const float *b1, const void *W2, const float *b2, const float *bn_scale,
                       const float *bn_shift, float *h_out, float *h_out_tf32, void *workspace,
                       size_t workspace_bytes, void *stream);
 

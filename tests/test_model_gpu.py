@@ -169,6 +169,16 @@ def test_dense_kernels_against_tf32_rounded_oracle():
                                                  None, p(ws), nbytes, _ops._stream()))
                 o64b = (h.double() + hid @ W2d.double().t() + b2.double()) * sc.double() + sh.double()
                 assert (out.cpu().double() - o64b).abs().max() < 1e-3, (M, 'round-in-kernel')
+                # kind::f16 variant: fp16 weights, operands packed to fp16 in the kernel, fp32 skip
+                W1h, W2h = W1.half().cuda(), W2.half().cuda()
+                out.fill_(float('nan'))
+                _lib.check(lib.gnngls_ff_forward(_ops.DENSE_TCGEN05_F16, p(hraw), None, M, p(W1h), p(b1c), p(W2h), p(b2c), p(scc),
+                                                 p(shc), p(out), None, p(ws), 0, _ops._stream()))
+                torch.cuda.synchronize()
+                h16, W116, W216 = h.half().double(), W1.half().double(), W2.half().double()
+                hid16 = torch.relu(h16 @ W116.t() + b1.double()).half().double()
+                o64h = (h.double() + hid16 @ W216.t() + b2.double()) * sc.double() + sh.double()
+                assert (out.cpu().double() - o64h).abs().max() < 1e-3, (M, 'f16 feed-forward')
 
 
 def test_glue_kernels_bit_exact():
@@ -300,13 +310,15 @@ def test_aggregate_kernels_all_storage_formats(n, B):
 
 
 def test_tf32_feature_storage_switch(monkeypatch):
-    """GNNGLS_FT_DTYPE=tf32 keeps the fp32-storage TF32 aggregate reachable from the model."""
+    """GNNGLS_FT_DTYPE=tf32 / GNNGLS_FF_DTYPE=tf32 keep the all-TF32 tensor-core kernels reachable from the model."""
     port, m = make_models()
     c = MODEL[0]
     n, B = c.nB.tolist()
     y16 = run(m, n, B, c.x, 'tcgen05', 'kn')
     monkeypatch.setenv('GNNGLS_FT_DTYPE', 'tf32')
+    monkeypatch.setenv('GNNGLS_FF_DTYPE', 'tf32')
     y32 = run(m, n, B, c.x, 'tcgen05', 'kn')
+    assert not np.array_equal(y16, y32)
     tol = tf32_budget(port, n, B, c.x, c.y64)
     assert np.abs(y32 - c.y64).max() <= tol and np.abs(y16 - c.y64).max() <= tol
 
