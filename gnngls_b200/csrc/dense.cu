@@ -42,6 +42,7 @@ struct EpiParams {
     const float *v2;     // FF2: bn_shift[128]
     const float *skip;   // FF2: h1 [M,128] (fp32, unrounded)
     int round_tf32;      // FC: store ft rounded to TF32; FF1 (debug path): same for the hidden activations
+    int skip_is_a;       // fused FF: the staged A operand is the skip tensor itself (same pointer)
 };
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -562,14 +563,18 @@ int launch_tc_gemm(const float *A, const float *W, const EpiParams &p, cudaStrea
 constexpr int FF_HC = 64;                              // hidden units per chunk
 constexpr int FF_CHUNKS = HID_ / FF_HC;                // 8
 constexpr int FF_WSTAGES = 7;
+constexpr int FF_WSTAGES_F16 = 4;                      // fp16 weights: one stage = a whole chunk of W1 or W2
 constexpr int FF_WSTAGE_BYTES = 16384;                 // half of W1c: 2 boxes [64 x 32]; half of W2c: 1 box [128 x 32]
 constexpr int FF_A_BYTES = BM * D_ * 4;                // 64 KB: 4 boxes [128 x 32]
-constexpr int FF_SVEC = 3 * D_ + HID_;                 // b2 | bn_scale | bn_shift | b1
+constexpr int FF_SVEC = 4 * D_ + HID_;                 // b2 | bn_scale | bn_shift | b1 | b2*bn_scale + bn_shift
 constexpr int FF_THREADS = 15 * 32;                    // warp0 W-TMA, warp1 MMA, warps 2..9 epilogue-1, warp10 A-TMA, warps 11..14 A staging + final epilogue
-constexpr int FF_NBARS = 4 + 2 * FF_WSTAGES + 8;
+constexpr int FF_NBARS = 4 + 2 * FF_WSTAGES + 8 + 4;
+constexpr int FF_THREADS_F16 = 19 * 32;                // fp16 variant: + warps 15..18, final epilogue only
 constexpr int FF_TMEM_COLS = 512;
-constexpr size_t FF_SMEM = 1024 + FF_A_BYTES + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES + 4 * STG_TILE_BYTES + FF_SVEC * 4 +
-                           FF_NBARS * 8 + 16;
+constexpr size_t ff_smem_bytes(bool f16) {
+    return 1024 + (f16 ? 2 : 1) * (size_t)FF_A_BYTES + (size_t)(f16 ? FF_WSTAGES_F16 : FF_WSTAGES) * FF_WSTAGE_BYTES +
+           4 * STG_TILE_BYTES + FF_SVEC * 4 + FF_NBARS * 8 + 16;
+}
 
 // kind::f16 instruction descriptor: F32 accumulate, A/B = F16 (format 0), K-major A and B
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
@@ -624,22 +629,30 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // (K = 16 per instruction: half the MMAs and half the streamed weight bytes; fp16 carries the same 10-bit
 // mantissa as the TF32 operands of the other variant, values saturate at +-65504).
 template <int CL, bool F16>      // CL: CTAs per cluster sharing (multicasting) the streamed weights: 1, 2 or 4
-__global__ void __launch_bounds__(FF_THREADS, 1)
+__global__ void __launch_bounds__(F16 ? FF_THREADS_F16 : FF_THREADS, 1)
 ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const EpiParams p, const float *__restrict__ b1,
                      const int round_a) {
     static_assert(!F16 || CL == 1, "the fp16 variant does not multicast");
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024B-aligned, still .shared
+    // fp16 variant: the weights need half the ring, which pays for a second A buffer: A(t) stays in shared memory
+    // until the final epilogue of tile t has taken its skip connection from it (no second trip to HBM for h1)
+    constexpr int WST = F16 ? FF_WSTAGES_F16 : FF_WSTAGES;
+    constexpr int NA = F16 ? 2 : 1;
     unsigned char *sA = smem;
-    unsigned char *sW = sA + FF_A_BYTES;
-    float *staging = reinterpret_cast<float *>(sW + (size_t)FF_WSTAGES * FF_WSTAGE_BYTES);
+    unsigned char *sW = sA + NA * FF_A_BYTES;
+    float *staging = reinterpret_cast<float *>(sW + (size_t)WST * FF_WSTAGE_BYTES);
     float *svec = staging + 4 * (STG_TILE_BYTES / 4);
     uint64_t *bars = reinterpret_cast<uint64_t *>(svec + FF_SVEC);
     uint64_t *a_full = bars, *a_empty = bars + 1, *at_full = bars + 2, *at_empty = bars + 3;
     uint64_t *w_full = bars + 4, *w_empty = w_full + FF_WSTAGES;
     uint64_t *d1_full = w_empty + FF_WSTAGES, *h_full = d1_full + 2, *d2_full = h_full + 2, *d2_empty = d2_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 2);
+    uint64_t *a_full2 = d2_empty + 2, *a_empty2 = d2_empty + 3;      // second A buffer in shared memory (fp16 variant)
+    uint64_t *at_full2 = d2_empty + 4, *at_empty2 = d2_empty + 5;    // second A buffer in tensor memory (fp16 variant)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 6);
+    constexpr int NTHREADS = F16 ? FF_THREADS_F16 : FF_THREADS;
+    const bool skip_smem = F16 && p.skip_is_a;                       // the staged operand IS the fp32 skip tensor
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Every CTA of a cluster walks the same number of tile groups (the weight ring is shared); a CTA whose
@@ -650,15 +663,20 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int64_t m_tiles = (m_tiles_real + CL - 1) / CL * CL;       // loops run `w < m_tiles` with w = tile0 + k*tile_step
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
 
-    for (int c = threadIdx.x; c < D_; c += FF_THREADS) { svec[c] = p.v0[c]; svec[D_ + c] = p.v1[c]; svec[2 * D_ + c] = p.v2[c]; }
-    for (int c = threadIdx.x; c < HID_; c += FF_THREADS) svec[3 * D_ + c] = b1[c];
+    for (int c = threadIdx.x; c < D_; c += NTHREADS) {
+        svec[c] = p.v0[c]; svec[D_ + c] = p.v1[c]; svec[2 * D_ + c] = p.v2[c];
+        svec[3 * D_ + HID_ + c] = fmaf(p.v0[c], p.v1[c], p.v2[c]);    // b2*scale + shift: (skip + acc + b2)*scale + shift in two ops
+    }
+    for (int c = threadIdx.x; c < HID_; c += NTHREADS) svec[3 * D_ + c] = b1[c];
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
-        mbar_init(a_full, 1); mbar_init(a_empty, 4); mbar_init(at_full, 4); mbar_init(at_empty, 1);
-        for (int s = 0; s < FF_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
+        constexpr int FE_WARPS = F16 ? 8 : 4;                 // warps that share a tile's final epilogue
+        mbar_init(a_full, 1); mbar_init(a_empty, F16 ? FE_WARPS : 4); mbar_init(at_full, 4); mbar_init(at_empty, 1);
+        mbar_init(a_full2, 1); mbar_init(a_empty2, FE_WARPS); mbar_init(at_full2, 4); mbar_init(at_empty2, 1);
+        for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
         for (int g = 0; g < 2; ++g) {
             mbar_init(&d1_full[g], 1); mbar_init(&h_full[g], EPI_WARPS);
-            mbar_init(&d2_full[g], 1); mbar_init(&d2_empty[g], 4);
+            mbar_init(&d2_full[g], 1); mbar_init(&d2_empty[g], F16 ? 8 : 4);
         }
         fence_barrier_init();
     }
@@ -668,16 +686,19 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (CL > 1) cluster_sync_all();                           // peers' barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tm_d2 = tmem_base, tm_dh = tmem_base + 256, tm_a = tmem_base + 384;
+    const uint32_t tm_d2 = tmem_base, tm_dh = tmem_base + 256, tm_a = tmem_base + 384;   // fp16: A[0] [384,448) | A[1] [448,512)
 
     if (warp == 10) {
         // ------------------------------------------------------------------ A-tile TMA producer
         if (lane == 0) {
             uint32_t it = 0;
             for (int64_t w = tile0; w < m_tiles; w += tile_step, ++it) {
-                mbar_wait(a_empty, (it & 1) ^ 1);             // the previous tile has been copied out of smem
-                mbar_expect_tx(a_full, FF_A_BYTES);
-                for (int kb = 0; kb < D_ / BK; ++kb) tma_load_2d(&tmA, a_full, sA + kb * (BM * BK * 4), kb * BK, (int)w * BM);
+                const uint32_t ab = F16 ? (it & 1) : 0, an = F16 ? (it >> 1) : it;     // buffer, use count of that buffer
+                uint64_t *af = ab ? a_full2 : a_full, *ae = ab ? a_empty2 : a_empty;
+                mbar_wait(ae, (an & 1) ^ 1);                  // the previous user of this buffer is done with it
+                mbar_expect_tx(af, FF_A_BYTES);
+                for (int kb = 0; kb < D_ / BK; ++kb)
+                    tma_load_2d(&tmA, af, sA + ab * FF_A_BYTES + kb * (BM * BK * 4), kb * BK, (int)w * BM);
             }
         }
     } else if (warp >= 11) {
@@ -685,31 +706,64 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        float *stg = staging + (warp - 11) * (STG_TILE_BYTES / 4);
-        auto final_epilogue = [&](int64_t w, uint32_t t) {    // tile index w, local tile counter t
+        float *stg = staging + ((warp - 11) & 3) * (STG_TILE_BYTES / 4);
+        // tile index w, local tile counter t, 32-column chunks [c_begin, c_end)
+        auto final_epilogue = [&](int64_t w, uint32_t t, int c_begin, int c_end) {
             const uint32_t d = t & 1;
             mbar_wait(&d2_full[d], (t >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c2 = 0; c2 < BN / 32; ++c2) {
+            for (int c2 = c_begin; c2 < c_end; ++c2) {
                 float v[32];
                 tmem_ld_32x32(tm_d2 + lane_sel + d * BN + c2 * 32, v);
-                epilogue_tile32<EPI_FF2>(p, svec, stg, w * BM + q * 32, c2 * 32, v, lane);
+                if (skip_smem) {
+                    // skip connection straight from the A tile still resident in shared memory (TMA 128B-swizzled
+                    // layout: k-block c2, row r, 16-byte pieces XOR-ed with r & 7), then the usual coalesced store
+                    // The 32-row x 128-byte block this warp reads has exactly the geometry of a staging tile, so the
+                    // results are written back in place and leave through the coalesced tile store.
+                    float *blk = reinterpret_cast<float *>(sA + (t & 1) * FF_A_BYTES + c2 * (BM * BK * 4) + q * 32 * 128);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 sk = *stg_slot(blk, lane, j);
+                        const float4 sc = *reinterpret_cast<const float4 *>(svec + D_ + c2 * 32 + 4 * j);
+                        const float4 sh = *reinterpret_cast<const float4 *>(svec + 3 * D_ + HID_ + c2 * 32 + 4 * j);
+                        float4 o;
+                        o.x = fmaf(sk.x + v[4 * j], sc.x, sh.x); o.y = fmaf(sk.y + v[4 * j + 1], sc.y, sh.y);
+                        o.z = fmaf(sk.z + v[4 * j + 2], sc.z, sh.z); o.w = fmaf(sk.w + v[4 * j + 3], sc.w, sh.w);
+                        *stg_slot(blk, lane, j) = o;
+                    }
+                    __syncwarp();
+                    stg_store_tile(blk, p.out, p.out_tf32, w * BM + q * 32, c2 * 32, D_, p.M, lane);
+                    __syncwarp();
+                } else {
+                    epilogue_tile32<EPI_FF2>(p, svec, stg, w * BM + q * 32, c2 * 32, v, lane);
+                }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&d2_empty[d]);
+            if (F16) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our smem writes before the next TMA into this buffer
+            if (lane == 0) {
+                mbar_arrive(&d2_empty[d]);
+                if (F16) mbar_arrive((t & 1) ? a_empty2 : a_empty);   // this tile's A buffer may be overwritten now
+            }
         };
+        if (F16 && warp >= 15) {
+            // ---- fp16 variant: warps 15..18 take output columns [0,64) of every tile's final epilogue; the staging
+            // warps 11..14 take [64,128) of the previous tile after they have put the next A into tensor memory
+            uint32_t it = 0;
+            for (int64_t w = tile0; w < m_tiles; w += tile_step, ++it) final_epilogue(w, it, 0, 2);
+        } else {
         uint32_t it = 0;
         int64_t w_prev = -1;
         for (int64_t w = tile0; w < m_tiles; w += tile_step, ++it) {
-            mbar_wait(a_full, it & 1);
-            mbar_wait(at_empty, (it & 1) ^ 1);                // GEMM1 of the previous tile has finished reading A[tmem]
+            const uint32_t ab = F16 ? (it & 1) : 0, an = F16 ? (it >> 1) : it;
+            mbar_wait(ab ? a_full2 : a_full, an & 1);
+            mbar_wait(ab ? at_empty2 : at_empty, (an & 1) ^ 1);   // GEMM1 of the previous user has finished reading this A[tmem]
             tc_fence_after();
 #pragma unroll 1
             for (int kb = 0; kb < D_ / BK; ++kb) {
                 float v[32];
-                const unsigned char *row = sA + kb * (BM * BK * 4) + r * 128;
+                const unsigned char *row = sA + ab * FF_A_BYTES + kb * (BM * BK * 4) + r * 128;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float4 x = *reinterpret_cast<const float4 *>(row + ((j ^ (r & 7)) << 4));
@@ -720,7 +774,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
-                    tmem_st_32x16(tm_a + lane_sel + kb * (BK / 2), pk);
+                    tmem_st_32x16(tm_a + ab * 64 + lane_sel + kb * (BK / 2), pk);
                 } else {
                     tmem_st_32x32(tm_a + lane_sel + kb * BK, v);
                 }
@@ -728,11 +782,15 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(a_empty); mbar_arrive(at_full); }
-            if (w_prev >= 0) final_epilogue(w_prev, it - 1);
+            if (lane == 0) {
+                if (!F16) mbar_arrive(a_empty);               // (fp16 variant: released by the tile's final epilogue)
+                mbar_arrive(ab ? at_full2 : at_full);
+            }
+            if (w_prev >= 0) final_epilogue(w_prev, it - 1, F16 ? 2 : 0, 4);
             w_prev = w;
         }
-        if (w_prev >= 0) final_epilogue(w_prev, it - 1);
+        if (w_prev >= 0) final_epilogue(w_prev, it - 1, F16 ? 2 : 0, 4);
+        }
     } else if (warp == 0) {
         // ------------------------------------------------------------------ weight producer (ring order == MMA order)
         if (lane == 0) {
@@ -751,7 +809,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int kk = (int)crank / per, r0 = ((int)crank % per) * BR;
                     tma_load_2d_mc(&tmW1, &w_full[stage], dst + kk * (FF_HC * BK * 4) + r0 * 128, (2 * half + kk) * BK, c * FF_HC + r0, kMask);
                 }
-                if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                if (++stage == WST) { stage = 0; phase ^= 1; }
             };
             auto load_w2 = [&](int c, int half) {             // all 128 outputs, hidden units [64c + 32*half, +32): [128 rows x 32 k]
                 mbar_wait(&w_empty[stage], phase ^ 1);
@@ -759,7 +817,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 mbar_expect_tx(&w_full[stage], FF_WSTAGE_BYTES);
                 if (CL == 1) tma_load_2d(&tmW2, &w_full[stage], dst, c * FF_HC + half * BK, 0);
                 else tma_load_2d_mc(&tmW2, &w_full[stage], dst + (int)crank * BR * 128, c * FF_HC + half * BK, (int)crank * BR, kMask);
-                if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                if (++stage == WST) { stage = 0; phase ^= 1; }
             };
             // fp16: one stage holds a whole chunk of W1 (2 boxes [64 units x 64 k]) or of W2 (1 box [128 outputs x 64 units])
             auto load_w1_f16 = [&](int c) {
@@ -767,13 +825,13 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 unsigned char *dst = sW + (size_t)stage * FF_WSTAGE_BYTES;
                 mbar_expect_tx(&w_full[stage], FF_WSTAGE_BYTES);
                 for (int kk = 0; kk < 2; ++kk) tma_load_2d(&tmW1, &w_full[stage], dst + kk * (FF_HC * 128), kk * 64, c * FF_HC);
-                if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                if (++stage == WST) { stage = 0; phase ^= 1; }
             };
             auto load_w2_f16 = [&](int c) {
                 mbar_wait(&w_empty[stage], phase ^ 1);
                 mbar_expect_tx(&w_full[stage], FF_WSTAGE_BYTES);
                 tma_load_2d(&tmW2, &w_full[stage], sW + (size_t)stage * FF_WSTAGE_BYTES, c * FF_HC, 0);
-                if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                if (++stage == WST) { stage = 0; phase ^= 1; }
             };
             for (int64_t w = tile0; w < m_tiles; w += tile_step) {
                 if (F16) {
@@ -814,7 +872,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         umma_commit(&w_empty[stage]);
                     }
                     __syncwarp();
-                    if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == WST) { stage = 0; phase ^= 1; }
                 } else {
 #pragma unroll 1
                     for (int half = 0; half < 2; ++half) {
@@ -828,11 +886,12 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             if (CL == 1) umma_commit(&w_empty[stage]); else umma_commit_mc(&w_empty[stage], kMask);
                         }
                         __syncwarp();
-                        if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == WST) { stage = 0; phase ^= 1; }
                     }
                 }
             };
-            mbar_wait(at_full, it & 1);                       // A tile is in TMEM
+            const uint32_t ab = F16 ? (it & 1) : 0, an = F16 ? (it >> 1) : it;
+            mbar_wait(ab ? at_full2 : at_full, an & 1);       // A tile is in TMEM
             for (int c = 0; c < FF_CHUNKS; ++c) {
                 const int g = c & 1;
                 if (F16) {
@@ -845,14 +904,14 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const uint64_t db = make_sw128_kmajor_desc(sw + kk * (FF_HC * 128));
 #pragma unroll
                             for (int k = 0; k < 4; ++k)       // k range [64kk + 16k, +16) = packed columns 32kk + 8k
-                                umma_f16_ts(tm_dh + g * FF_HC, tm_a + kk * 32 + 8 * k, db + (uint64_t)(2 * k), idesc1, (kk | k) != 0);
+                                umma_f16_ts(tm_dh + g * FF_HC, tm_a + ab * 64 + kk * 32 + 8 * k, db + (uint64_t)(2 * k), idesc1, (kk | k) != 0);
                         }
                         umma_commit(&w_empty[stage]);
                         umma_commit(&d1_full[g]);
-                        if (c == FF_CHUNKS - 1) umma_commit(at_empty);   // last reader of A[tmem]
+                        if (c == FF_CHUNKS - 1) umma_commit(ab ? at_empty2 : at_empty);   // last reader of this A[tmem]
                     }
                     __syncwarp();
-                    if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == WST) { stage = 0; phase ^= 1; }
                 } else {
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
@@ -875,7 +934,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                     __syncwarp();
-                    if (++stage == FF_WSTAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == WST) { stage = 0; phase ^= 1; }
                 }
                 }
                 if (c == 1) { mbar_wait(&d2_empty[d], ((it >> 1) & 1) ^ 1); tc_fence_after(); }   // final epilogue two tiles back drained D2[d]
@@ -948,7 +1007,7 @@ int launch_ff_fused_cl(const float *a_op, int round_a, const void *W1, const flo
         if (int rc = make_map(&tmW2, static_cast<const float *>(W2), D_, HID_, CL == 1 ? BM : 128 / CL)) return rc;
     }
     auto kern = ff_fused_kernel<CL, F16>;
-    GNNGLS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
+    GNNGLS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes(F16)));
     const int64_t tiles = (p.M + BM - 1) / BM;
     const int sms = gnngls::device_sm_count();
     int64_t grid = tiles < sms ? tiles : sms;
@@ -956,8 +1015,8 @@ int launch_ff_fused_cl(const float *a_op, int round_a, const void *W1, const flo
     if (grid > sms) grid = sms / CL * CL;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(FF_THREADS);
-    cfg.dynamicSmemBytes = FF_SMEM;
+    cfg.blockDim = dim3(F16 ? FF_THREADS_F16 : FF_THREADS);
+    cfg.dynamicSmemBytes = ff_smem_bytes(F16);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1140,7 +1199,10 @@ extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32
     if (impl == GNNGLS_DENSE_TCGEN05)
         return launch_ff_fused(a1, h1_tf32 == nullptr, W1, b1, W2, p2, st, false);   // no pre-rounded copy: round while staging
     if (impl == GNNGLS_DENSE_TCGEN05_F16)
+    {
+        p2.skip_is_a = 1;
         return launch_ff_fused(h1, 0, W1, b1, W2, p2, st, true);                     // fp16 weights; h1 is packed to fp16 while staging
+    }
     if (impl == GNNGLS_DENSE_SIMT) {
         if (int rc = launch_simt_gemm<HID_, D_, EPI_FF1>(a1, static_cast<const float *>(W1), p1, st)) return rc;
         return launch_simt_gemm<D_, HID_, EPI_FF2>(hid, static_cast<const float *>(W2), p2, st);
