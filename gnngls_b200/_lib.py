@@ -40,13 +40,13 @@ SIGNATURES = {
     'gnngls_nn_init_batch': (_i, [_i, _p, _p, _i, _i, _i, _p, _p, _p]),
     'gnngls_tour_cost_batch': (_i, [_p, _p, _i, _i, _p, _p]),
     'gnngls_edge_features': (_i, [_p, _i, _i, _d, _d, _p, _p]),
-    'gnngls_embed_forward': (_i, [_p, _i64, _i, _p, _p, _p, _p, _p]),
+    'gnngls_embed_forward': (_i, [_p, _i64, _i, _p, _p, _p, _p, _i, _p]),
     'gnngls_fc_forward': (_i, [_i, _p, _i64, _p, _p, _p, _p, _i, _p, _p, _p]),
     'gnngls_gat_aggregate_csr': (_i, [_p, _p, _i64, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'gnngls_gat_kn_workspace_bytes': (_sz, [_i, _i]),
     'gnngls_gat_aggregate_kn': (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     'gnngls_ff_workspace_bytes': (_sz, [_i, _i64]),
-    'gnngls_ff_forward': (_i, [_i, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    'gnngls_ff_forward': (_i, [_i, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     'gnngls_decision_forward': (_i, [_p, _i64, _i, _p, _p, _p, _p]),
     'gnngls_regret_postprocess': (_i, [_p, _i64, _d, _d, _p, _p]),
 }

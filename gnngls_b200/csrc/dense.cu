@@ -35,7 +35,8 @@ struct EpiParams {
     int64_t M;
     float *out;          // FC: ft [M,128]; FF1: hid [M,512]; FF2: h_out [M,128]
     __half *out_f16;     // FC only (nullable): store ft as fp16 [M,128] instead of fp32 `out`
-    float *out_tf32;     // FF2 only (nullable): copy of h_out rounded to TF32 for the next tensor-core GEMM
+    float *out_tf32;     // FF2 only (nullable): operand copy of h_out for the next tensor-core GEMM: fp32 rounded to TF32,
+    int out_op_f16;      //   or (out_op_f16 != 0) the same pointer is a __half array and the copy is fp16
     float *el, *er;      // FC only, [M,8]
     const float *v0;     // FC: attn_l[128]; FF1: b1[512]; FF2: b2[128]
     const float *v1;     // FC: attn_r[128]; FF2: bn_scale[128]
@@ -58,6 +59,12 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+}
+
+// operand copy of 4 consecutive activations at element offset `idx`: TF32-rounded fp32 or fp16
+__device__ __forceinline__ void store_op_copy(float *base, int f16, int64_t idx, float4 v) {
+    if (f16) *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(base) + idx) = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
+    else *reinterpret_cast<float4 *>(base + idx) = tf32_rna4(v);
 }
 
 // Fused epilogue for 4 consecutive columns [col, col+4) of one row (SIMT debug GEMM).  Called with a
@@ -99,7 +106,7 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams &p, int64_t row, i
         o.x = (s.x + (acc.x + b.x)) * sc.x + sh.x; o.y = (s.y + (acc.y + b.y)) * sc.y + sh.y;
         o.z = (s.z + (acc.z + b.z)) * sc.z + sh.z; o.w = (s.w + (acc.w + b.w)) * sc.w + sh.w;
         *reinterpret_cast<float4 *>(p.out + row * D_ + col) = o;
-        if (p.out_tf32) *reinterpret_cast<float4 *>(p.out_tf32 + row * D_ + col) = tf32_rna4(o);
+        if (p.out_tf32) store_op_copy(p.out_tf32, p.out_op_f16, row * D_ + col, o);
     }
 }
 
@@ -123,14 +130,14 @@ __device__ __forceinline__ void stg_load_tile(float *stg, const float *src, int6
 }
 // staging -> coalesced global (optionally a second, TF32-rounded copy)
 __device__ __forceinline__ void stg_store_tile(const float *stg, float *dst, float *dst_tf32, int64_t row0, int col0, int ld,
-                                               int64_t M, int lane) {
+                                               int64_t M, int lane, int op_f16 = 0) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int r = it * 4 + (lane >> 3), pc = lane & 7;
         if (row0 + r < M) {
             const float4 v = *stg_slot(const_cast<float *>(stg), r, pc);
             *reinterpret_cast<float4 *>(dst + (row0 + r) * ld + col0 + 4 * pc) = v;
-            if (dst_tf32) *reinterpret_cast<float4 *>(dst_tf32 + (row0 + r) * ld + col0 + 4 * pc) = tf32_rna4(v);
+            if (dst_tf32) store_op_copy(dst_tf32, op_f16, (row0 + r) * ld + col0 + 4 * pc, v);
         }
     }
 }
@@ -212,7 +219,7 @@ __device__ __forceinline__ void epilogue_tile32(const EpiParams &p, const float 
             *stg_slot(stg, lane, j) = r;
         }
         __syncwarp();
-        stg_store_tile(stg, p.out, p.out_tf32, row0, col, D_, p.M, lane);
+        stg_store_tile(stg, p.out, p.out_tf32, row0, col, D_, p.M, lane, p.out_op_f16);
         __syncwarp();
     }
 }
@@ -292,6 +299,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, issued by one thread
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 operands, K = 16 per instruction)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
@@ -347,6 +363,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 instruction descriptor: F32 accumulate, A/B = F16 (format 0), K-major A and B
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ================================================================================================
 // tcgen05 GEMM:  C[M, N_TOTAL] = A[M, K_TOTAL] * W[N_TOTAL, K_TOTAL]^T  with fused epilogue
 // ================================================================================================
@@ -360,10 +381,12 @@ constexpr int SVEC_FLOATS = 512;                     // per-column epilogue vect
 constexpr int STG_TILE_BYTES = 32 * 32 * 4;              // per-warp epilogue staging tile
 constexpr size_t GEMM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_WARPS * STG_TILE_BYTES + SVEC_FLOATS * 4 + 256;
 
-template <int N_TOTAL, int K_TOTAL, int EPI>
+// F16: both operands are fp16 in global memory (a 128-byte swizzle row then holds 64 k), MMAs are kind::f16
+template <int N_TOTAL, int K_TOTAL, int EPI, bool F16 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams p) {
-    constexpr int KB = K_TOTAL / BK;
+    constexpr int BKE = F16 ? 2 * BK : BK;               // k elements per 128-byte row
+    constexpr int KB = K_TOTAL / BKE;
     constexpr int NB = N_TOTAL / BN;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024B-aligned, still .shared
@@ -409,15 +432,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char *sa = stage_base + (size_t)stage * STAGE_BYTES;
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    tma_load_2d(&tmA, &full[stage], sa, kb * BK, m_blk * BM);
-                    tma_load_2d(&tmB, &full[stage], sa + BM * BK * 4, kb * BK, n_blk * BN);
+                    tma_load_2d(&tmA, &full[stage], sa, kb * BKE, m_blk * BM);
+                    tma_load_2d(&tmB, &full[stage], sa + BM * BK * 4, kb * BKE, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (warp-uniform control flow)
-        constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+        constexpr uint32_t idesc = F16 ? make_idesc_f16(BM, BN) : make_idesc_tf32(BM, BN);
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
         for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
             mbar_wait(&tempty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
@@ -431,8 +454,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint64_t db = make_sw128_kmajor_desc(sa + BM * BK * 4);
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k)         // UMMA_K = 8 for tf32: 32 bytes along K
-                        umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    for (int k = 0; k < BK / 8; ++k) {       // one MMA per 32 bytes along K: 8 tf32 or 16 fp16 values
+                        if (F16) umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        else umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty[stage]);              // frees the smem slot when these MMAs finish
                     if (kb == KB - 1) umma_commit(&tfull[acc]);
                 }
@@ -524,12 +549,17 @@ int make_map_f16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t col
     return GNNGLS_OK;
 }
 
-template <int N_TOTAL, int K_TOTAL, int EPI>
-int launch_tc_gemm(const float *A, const float *W, const EpiParams &p, cudaStream_t st) {
+template <int N_TOTAL, int K_TOTAL, int EPI, bool F16 = false>
+int launch_tc_gemm(const void *A, const void *W, const EpiParams &p, cudaStream_t st) {
     CUtensorMap tmA, tmB;
-    if (int rc = make_map(&tmA, A, (uint64_t)p.M, K_TOTAL)) return rc;
-    if (int rc = make_map(&tmB, W, N_TOTAL, K_TOTAL)) return rc;
-    auto kern = gemm_tf32_kernel<N_TOTAL, K_TOTAL, EPI>;
+    if (F16) {
+        if (int rc = make_map_f16(&tmA, A, (uint64_t)p.M, K_TOTAL, BM)) return rc;
+        if (int rc = make_map_f16(&tmB, W, N_TOTAL, K_TOTAL, BN)) return rc;
+    } else {
+        if (int rc = make_map(&tmA, static_cast<const float *>(A), (uint64_t)p.M, K_TOTAL)) return rc;
+        if (int rc = make_map(&tmB, static_cast<const float *>(W), N_TOTAL, K_TOTAL)) return rc;
+    }
+    auto kern = gemm_tf32_kernel<N_TOTAL, K_TOTAL, EPI, F16>;
     GNNGLS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     const int64_t work = ((p.M + BM - 1) / BM) * (N_TOTAL / BN);
     const int sms = gnngls::device_sm_count();
@@ -576,10 +606,6 @@ constexpr size_t ff_smem_bytes(bool f16) {
            4 * STG_TILE_BYTES + FF_SVEC * 4 + FF_NBARS * 8 + 16;
 }
 
-// kind::f16 instruction descriptor: F32 accumulate, A/B = F16 (format 0), K-major A and B
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 // D[tmem] (+)= A[tmem] * B[smem]^T, kind::f16: K = 16 per instruction, A: lane = row, one 32-bit column per PAIR of k
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -733,7 +759,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         *stg_slot(blk, lane, j) = o;
                     }
                     __syncwarp();
-                    stg_store_tile(blk, p.out, p.out_tf32, w * BM + q * 32, c2 * 32, D_, p.M, lane);
+                    stg_store_tile(blk, p.out, p.out_tf32, w * BM + q * 32, c2 * 32, D_, p.M, lane, p.out_op_f16);
                     __syncwarp();
                 } else {
                     epilogue_tile32<EPI_FF2>(p, svec, stg, w * BM + q * 32, c2 * 32, v, lane);
@@ -1094,7 +1120,7 @@ int launch_simt_gemm(const float *A, const float *W, const EpiParams &p, cudaStr
 // embed_layer / decision_layer
 // ================================================================================================
 __global__ void embed_kernel(const float *__restrict__ x, int64_t M, int in_dim, const float *__restrict__ W,
-                             const float *__restrict__ b, float *__restrict__ h, float *__restrict__ h_tf32) {
+                             const float *__restrict__ b, float *__restrict__ h, float *__restrict__ h_tf32, int op_f16) {
     // one warp per node, lane owns 4 output channels
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1109,7 +1135,7 @@ __global__ void embed_kernel(const float *__restrict__ x, int64_t M, int in_dim,
             o.w = fmaf(xv, W[(4 * lane + 3) * in_dim + k], o.w);
         }
         *reinterpret_cast<float4 *>(h + m * D_ + 4 * lane) = o;
-        if (h_tf32) *reinterpret_cast<float4 *>(h_tf32 + m * D_ + 4 * lane) = tf32_rna4(o);
+        if (h_tf32) store_op_copy(h_tf32, op_f16, m * D_ + 4 * lane, o);
     }
 }
 
@@ -1139,11 +1165,14 @@ int elementwise_grid(int64_t warps_needed, int threads) {
 }  // namespace
 
 extern "C" int gnngls_embed_forward(const float *x, int64_t M, int in_dim, const float *W, const float *b, float *h,
-                                    float *h_tf32, void *stream) {
+                                    void *h_op, int op_dtype, void *stream) {
     GNNGLS_REQUIRE(x && W && b && h, GNNGLS_ERR_BAD_ARG, "null pointer argument");
+    GNNGLS_REQUIRE(!h_op || op_dtype == GNNGLS_FT_TF32 || op_dtype == GNNGLS_FT_F16, GNNGLS_ERR_BAD_ARG, "operand copy must be TF32 or fp16");
+    float *h_tf32 = static_cast<float *>(h_op);
+    const int op_f16 = op_dtype == GNNGLS_FT_F16;
     GNNGLS_REQUIRE(in_dim >= 1, GNNGLS_ERR_BAD_ARG, "in_dim must be >= 1");
     if (M <= 0) return GNNGLS_OK;
-    embed_kernel<<<elementwise_grid(M, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, M, in_dim, W, b, h, h_tf32);
+    embed_kernel<<<elementwise_grid(M, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, M, in_dim, W, b, h, h_tf32, op_f16);
     GNNGLS_LAUNCH_OK("embed_kernel");
     return GNNGLS_OK;
 }
@@ -1158,7 +1187,7 @@ extern "C" int gnngls_decision_forward(const float *h, int64_t M, int out_dim, c
     return GNNGLS_OK;
 }
 
-extern "C" int gnngls_fc_forward(int impl, const float *h, int64_t M, const float *Wfc, const float *attn_l,
+extern "C" int gnngls_fc_forward(int impl, const void *h, int64_t M, const void *Wfc, const float *attn_l,
                                  const float *attn_r, void *ft, int ft_dtype, float *el, float *er, void *stream) {
     GNNGLS_REQUIRE(h && Wfc && attn_l && attn_r && ft && el && er, GNNGLS_ERR_BAD_ARG, "null pointer argument");
     GNNGLS_REQUIRE(ft_dtype == GNNGLS_FT_F32 || ft_dtype == GNNGLS_FT_TF32 || ft_dtype == GNNGLS_FT_F16, GNNGLS_ERR_BAD_ARG,
@@ -1171,7 +1200,8 @@ extern "C" int gnngls_fc_forward(int impl, const float *h, int64_t M, const floa
     p.round_tf32 = ft_dtype == GNNGLS_FT_TF32;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (impl == GNNGLS_DENSE_TCGEN05) return launch_tc_gemm<D_, D_, EPI_FC>(h, Wfc, p, st);
-    if (impl == GNNGLS_DENSE_SIMT) return launch_simt_gemm<D_, D_, EPI_FC>(h, Wfc, p, st);
+    if (impl == GNNGLS_DENSE_TCGEN05_F16) return launch_tc_gemm<D_, D_, EPI_FC, true>(h, Wfc, p, st);      // h and Wfc are fp16
+    if (impl == GNNGLS_DENSE_SIMT) return launch_simt_gemm<D_, D_, EPI_FC>(static_cast<const float *>(h), static_cast<const float *>(Wfc), p, st);
     GNNGLS_REQUIRE(false, GNNGLS_ERR_BAD_ARG, "unknown dense impl %d", impl);
 }
 
@@ -1182,9 +1212,11 @@ extern "C" size_t gnngls_ff_workspace_bytes(int impl, int64_t M) {
 
 extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32, int64_t M, const void *W1,
                                  const float *b1, const void *W2, const float *b2, const float *bn_scale,
-                                 const float *bn_shift, float *h_out, float *h_out_tf32, void *workspace,
+                                 const float *bn_shift, float *h_out, void *h_out_op, int op_dtype, void *workspace,
                                  size_t workspace_bytes, void *stream) {
     GNNGLS_REQUIRE(h1 && W1 && b1 && W2 && b2 && bn_scale && bn_shift && h_out, GNNGLS_ERR_BAD_ARG, "null pointer argument");
+    GNNGLS_REQUIRE(!h_out_op || op_dtype == GNNGLS_FT_TF32 || op_dtype == GNNGLS_FT_F16, GNNGLS_ERR_BAD_ARG, "operand copy must be TF32 or fp16");
+    float *h_out_tf32 = static_cast<float *>(h_out_op);
     if (M <= 0) return GNNGLS_OK;
     const size_t need = gnngls_ff_workspace_bytes(impl, M);
     GNNGLS_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), GNNGLS_ERR_WORKSPACE,
@@ -1194,7 +1226,7 @@ extern "C" int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32
     EpiParams p1{};
     p1.M = M; p1.out = hid; p1.v0 = b1;
     EpiParams p2{};
-    p2.M = M; p2.out = h_out; p2.out_tf32 = h_out_tf32; p2.v0 = b2; p2.v1 = bn_scale; p2.v2 = bn_shift; p2.skip = h1;
+    p2.M = M; p2.out = h_out; p2.out_tf32 = h_out_tf32; p2.out_op_f16 = op_dtype == GNNGLS_FT_F16; p2.v0 = b2; p2.v1 = bn_scale; p2.v2 = bn_shift; p2.skip = h1;
     const float *a1 = h1_tf32 ? h1_tf32 : h1;                 // GEMM operand; the skip path always reads fp32 h1
     if (impl == GNNGLS_DENSE_TCGEN05)
         return launch_ff_fused(a1, h1_tf32 == nullptr, W1, b1, W2, p2, st, false);   // no pre-rounded copy: round while staging

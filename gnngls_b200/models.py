@@ -92,6 +92,13 @@ def tf32_round(t):
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+def _op_f16():
+    """Tensor-core path: operand copies / weights travel as fp16 unless GNNGLS_OP_DTYPE=tf32 (or the older
+    GNNGLS_FF_DTYPE=tf32) asks for the all-TF32 kernels."""
+    return (os.environ.get('GNNGLS_OP_DTYPE', 'f16').lower() != 'tf32'
+            and os.environ.get('GNNGLS_FF_DTYPE', 'f16').lower() != 'tf32')
+
+
 def _bn_affine(bn):
     """Eval-mode BatchNorm1d as y = x*scale + shift (models.py:27,35)."""
     with torch.no_grad():
@@ -117,7 +124,7 @@ def _gat_block(G, h_op, skip, Wfc, al, ar, bias, bn_scale, bn_shift, dense_impl,
     lib = _lib.load()
     M, dev = h_op.shape[0], h_op.device
     st = _ops._stream()
-    tc = dense_impl == _ops.DENSE_TCGEN05
+    tc = dense_impl in (_ops.DENSE_TCGEN05, _ops.DENSE_TCGEN05_F16)
     # tensor-core path: ft travels as fp16 (same mantissa as the TF32 operand it would be rounded to, half the
     # bytes); GNNGLS_FT_DTYPE=tf32 keeps fp32 storage.  The fp32 debug path keeps ft exact.
     if not tc:
@@ -175,7 +182,7 @@ class AttentionLayer(nn.Module):
                  W1=f(ff[0].weight), b1=f(ff[0].bias), W2=f(ff[2].weight), b2=f(ff[2].bias), s2=s2, t2=t2)
         for k in ('Wfc', 'W1', 'W2'):
             d[k + '_tf32'] = tf32_round(d[k])
-        for k in ('W1', 'W2'):                              # fp16 feed-forward variant (same 10-bit mantissa as TF32)
+        for k in ('Wfc', 'W1', 'W2'):                       # fp16 variants (same 10-bit mantissa as TF32)
             d[k + '_f16'] = d[k].clamp(-65504.0, 65504.0).to(torch.float16).contiguous()
         return d
 
@@ -193,25 +200,24 @@ class AttentionLayer(nn.Module):
         impl = _dense_impl if _dense_impl is not None else (
             _ops.DENSE_SIMT if _dense_impl_default() == 'simt' else _ops.DENSE_TCGEN05)
         tc = impl == _ops.DENSE_TCGEN05
+        f16 = tc and _op_f16()
         x = x.contiguous()
         M, dev = x.shape[0], x.device
-        sfx = '_tf32' if tc else ''
+        sfx = '_f16' if f16 else ('_tf32' if tc else '')
+        op_impl = _ops.DENSE_TCGEN05_F16 if f16 else impl
+        op_dtype = _ops.FT_F16 if f16 else _ops.FT_TF32
         if tc and _x_tf32 is None:
-            _x_tf32 = tf32_round(x)
+            _x_tf32 = x.clamp(-65504.0, 65504.0).to(torch.float16) if f16 else tf32_round(x)
         h1, h1r = _gat_block(G, _x_tf32 if tc else x, x, prm['Wfc' + sfx], prm['al'], prm['ar'], prm['gbias'],
-                             prm['s1'], prm['t1'], impl, _gat_impl, ws)
-        nbytes = lib.gnngls_ff_workspace_bytes(impl, M)
+                             prm['s1'], prm['t1'], op_impl, _gat_impl, ws)
+        nbytes = lib.gnngls_ff_workspace_bytes(op_impl, M)
         wk = _buf(ws, 'ff_ws', (nbytes,), torch.uint8, dev)
         out = _out if _out is not None else torch.empty(M, 128, dtype=torch.float32, device=dev)
         p = _ops._ptr
-        # tensor-core path: the feed-forward runs as kind::f16 unless GNNGLS_FF_DTYPE=tf32
-        ff_impl, wsfx = impl, sfx
-        if tc and os.environ.get('GNNGLS_FF_DTYPE', 'f16').lower() != 'tf32':
-            ff_impl, wsfx = _ops.DENSE_TCGEN05_F16, '_f16'
         with stage('ff'):
-            _lib.check(lib.gnngls_ff_forward(ff_impl, p(h1), p(h1r), M, p(prm['W1' + wsfx]), p(prm['b1']),
-                                             p(prm['W2' + wsfx]), p(prm['b2']), p(prm['s2']), p(prm['t2']), p(out),
-                                             p(_out_tf32), p(wk), nbytes, _ops._stream()))
+            _lib.check(lib.gnngls_ff_forward(op_impl, p(h1), p(h1r), M, p(prm['W1' + sfx]), p(prm['b1']),
+                                             p(prm['W2' + sfx]), p(prm['b2']), p(prm['s2']), p(prm['t2']), p(out),
+                                             p(_out_tf32), op_dtype, p(wk), nbytes, _ops._stream()))
         return out
 
 
@@ -266,13 +272,15 @@ class EdgePropertyPredictionModel(nn.Module):
         p = _ops._ptr
         with torch.cuda.device(dev):
             tc = impl == _ops.DENSE_TCGEN05
+            f16 = tc and _op_f16()
+            op_t = torch.float16 if f16 else torch.float32     # operand copies of the activations for the fc GEMMs
             ha = _buf(self._ws, 'ha', (M, 128), torch.float32, dev)
             hb = _buf(self._ws, 'hb', (M, 128), torch.float32, dev)
-            har = _buf(self._ws, 'ha_tf32', (M, 128), torch.float32, dev) if tc else None
-            hbr = _buf(self._ws, 'hb_tf32', (M, 128), torch.float32, dev) if tc else None
+            har = _buf(self._ws, 'ha_op', (M, 128), op_t, dev) if tc else None
+            hbr = _buf(self._ws, 'hb_op', (M, 128), op_t, dev) if tc else None
             with stage('embed'):
                 _lib.check(lib.gnngls_embed_forward(p(x), M, in_dim, p(prm['We']), p(prm['be']), p(ha), p(har),
-                                                    _ops._stream()))
+                                                    _ops.FT_F16 if f16 else _ops.FT_TF32, _ops._stream()))
             cur, nxt, cur_r, nxt_r = ha, hb, har, hbr
             for layer, lp in zip(self.message_passing_layers, prm['layers']):
                 layer(G, cur, _params=lp, _ws=self._ws, _dense_impl=impl, _gat_impl=self.gat_impl, _out=nxt,

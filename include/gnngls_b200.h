@@ -143,38 +143,42 @@ int gnngls_tour_cost_batch(const double *D, const int32_t *tours, int B, int n, 
  * step is evaluated in fp64 and rounded to fp32 — verified against sklearn in tests). */
 int gnngls_edge_features(const double *D, int B, int n, double scale, double min_, float *x, void *stream);
 
-/* embed_layer (models.py:57,66): h[M,128] = x[M,in_dim] * W[128,in_dim]^T + b */
-int gnngls_embed_forward(const float *x, int64_t M, int in_dim, const float *W, const float *b,
-                         float *h, float *h_tf32 /* or NULL */, void *stream);
-
-/* dense implementation selector for the fc / feed-forward contractions */
-typedef enum gnngls_dense_impl {
-    GNNGLS_DENSE_TCGEN05 = 0,   /* TMA-fed tcgen05.mma kind::tf32, accumulators in TMEM (default) */
-    GNNGLS_DENSE_SIMT = 1,      /* plain fp32 CUDA-core kernel: debug cross-check only            */
-    GNNGLS_DENSE_TCGEN05_F16 = 2 /* feed-forward only: tcgen05.mma kind::f16, W1/W2 passed as fp16 */
-} gnngls_dense_impl;
-
-/* storage format of the projected features ft[M,128] handed from fc to the aggregates */
+/* storage format of a tensor-core operand in HBM: the projected features ft[M,128] handed from fc to the
+ * aggregates, and the operand copies of the activations (below) */
 typedef enum gnngls_ft_dtype {
     GNNGLS_FT_F32 = 0,    /* fp32, unrounded (pure-fp32 debug path)                                   */
     GNNGLS_FT_TF32 = 1,   /* fp32 storage, values rounded to TF32 (10-bit mantissa)                   */
     GNNGLS_FT_F16 = 2     /* IEEE fp16 (same 10-bit mantissa, half the bytes; saturates at +-65504)   */
 } gnngls_ft_dtype;
 
+/* embed_layer (models.py:57,66): h[M,128] = x[M,in_dim] * W[128,in_dim]^T + b
+ * h_op (nullable): operand copy of h for the first fc, as op_dtype says (GNNGLS_FT_TF32 or GNNGLS_FT_F16). */
+int gnngls_embed_forward(const float *x, int64_t M, int in_dim, const float *W, const float *b,
+                         float *h, void *h_op, int op_dtype, void *stream);
+
+/* dense implementation selector for the fc / feed-forward contractions */
+typedef enum gnngls_dense_impl {
+    GNNGLS_DENSE_TCGEN05 = 0,   /* TMA-fed tcgen05.mma kind::tf32, accumulators in TMEM (default) */
+    GNNGLS_DENSE_SIMT = 1,      /* plain fp32 CUDA-core kernel: debug cross-check only            */
+    GNNGLS_DENSE_TCGEN05_F16 = 2 /* tcgen05.mma kind::f16: weights (and the fc input) passed as fp16  */
+} gnngls_dense_impl;
+
 /* GATConv.fc + attention scores (Appendix A of SURVEY.md):
  *   ft[M,128] = h * Wfc[128,128]^T ; el[M,8] = log2(e) * sum_f ft*attn_l ; er[M,8] = log2(e) * sum_f ft*attn_r
  * The scores are stored in the log2 domain because the aggregates evaluate the edge softmax with ex2;
  * leaky_relu is positively homogeneous so softmax(leaky_relu(el+er)) is unchanged.  el/er are always
  * computed from the unrounded fp32 accumulators; `ft` is stored as `ft_dtype` says (its only consumer
- * is the aggregate, whose tensor-core operand has a 10-bit mantissa anyway).                        */
-int gnngls_fc_forward(int impl, const float *h, int64_t M, const float *Wfc, const float *attn_l,
+ * is the aggregate, whose tensor-core operand has a 10-bit mantissa anyway).
+ * h / Wfc: fp32 (GNNGLS_DENSE_SIMT: exact; GNNGLS_DENSE_TCGEN05: the TF32-rounded copies) or fp16
+ * (GNNGLS_DENSE_TCGEN05_F16: the fp16 operand copy written by embed / feed-forward, fp16 weights).    */
+int gnngls_fc_forward(int impl, const void *h, int64_t M, const void *Wfc, const float *attn_l,
                       const float *attn_r, void *ft, int ft_dtype, float *el, float *er, void *stream);
 
 /* Per-channel affine form of eval-mode BatchNorm1d: y = x*scale + shift
  * (scale = gamma/sqrt(var+eps), shift = beta - mean*scale; models.py:27,35).
  *
- * *_tf32 outputs (embed / aggregate / feed-forward, all nullable): a second copy of the produced
- * activation rounded to TF32 (cvt.rna).  The tcgen05 kind::tf32 MMA ignores the low 13 mantissa
+ * *_tf32 / *_op outputs (embed / aggregate / feed-forward, all nullable): a second copy of the produced
+ * activation for the next tensor-core GEMM: fp32 rounded to TF32 (cvt.rna), or fp16 (same mantissa, half the bytes).  The tcgen05 kind::tf32 MMA ignores the low 13 mantissa
  * bits of its operands (truncation, a biased error ~10x larger than rounding over this 8-layer
  * model); feeding it the pre-rounded copy makes that truncation exact, while skip connections keep
  * reading the unrounded fp32 activation.  Pass NULL on the pure-fp32 debug path. */
@@ -206,7 +210,7 @@ int gnngls_gat_aggregate_kn(int B, int n, const void *ft, int ft_dtype, const fl
 size_t gnngls_ff_workspace_bytes(int impl, int64_t M);
 int gnngls_ff_forward(int impl, const float *h1, const float *h1_tf32, int64_t M, const void *W1,
                       const float *b1, const void *W2, const float *b2, const float *bn_scale,
-                      const float *bn_shift, float *h_out, float *h_out_tf32, void *workspace,
+                      const float *bn_shift, float *h_out, void *h_out_op, int op_dtype, void *workspace,
                       size_t workspace_bytes, void *stream);
 
 /* decision_layer (models.py:63,69): y[M,out_dim] = h * Wd[out_dim,128]^T + bd */

@@ -155,7 +155,7 @@ def test_dense_kernels_against_tf32_rounded_oracle():
             out = torch.empty(M, 128, device='cuda')
             out_r = torch.empty(M, 128, device='cuda')
             _lib.check(lib.gnngls_ff_forward(impl, p(hd), p(hd), M, p(W1c), p(b1c), p(W2c), p(b2c), p(scc), p(shc), p(out),
-                                             p(out_r), p(ws), nbytes, _ops._stream()))
+                                             p(out_r), _ops.FT_TF32, p(ws), nbytes, _ops._stream()))
             torch.cuda.synchronize()
             hid = torch.relu(hh.double() @ W1d.double().t() + b1.double())
             if tc:
@@ -166,19 +166,33 @@ def test_dense_kernels_against_tf32_rounded_oracle():
             if tc:      # no pre-rounded operand copy: the kernel rounds h while staging, the skip stays unrounded fp32
                 hraw = h.cuda()
                 _lib.check(lib.gnngls_ff_forward(impl, p(hraw), None, M, p(W1c), p(b1c), p(W2c), p(b2c), p(scc), p(shc), p(out),
-                                                 None, p(ws), nbytes, _ops._stream()))
+                                                 None, _ops.FT_TF32, p(ws), nbytes, _ops._stream()))
                 o64b = (h.double() + hid @ W2d.double().t() + b2.double()) * sc.double() + sh.double()
                 assert (out.cpu().double() - o64b).abs().max() < 1e-3, (M, 'round-in-kernel')
                 # kind::f16 variant: fp16 weights, operands packed to fp16 in the kernel, fp32 skip
                 W1h, W2h = W1.half().cuda(), W2.half().cuda()
                 out.fill_(float('nan'))
+                out_h = torch.empty(M, 128, device='cuda', dtype=torch.float16)
                 _lib.check(lib.gnngls_ff_forward(_ops.DENSE_TCGEN05_F16, p(hraw), None, M, p(W1h), p(b1c), p(W2h), p(b2c), p(scc),
-                                                 p(shc), p(out), None, p(ws), 0, _ops._stream()))
+                                                 p(shc), p(out), p(out_h), _ops.FT_F16, p(ws), 0, _ops._stream()))
                 torch.cuda.synchronize()
+                assert torch.equal(out_h.cpu(), out.cpu().half())           # fp16 operand copy for the next fc
                 h16, W116, W216 = h.half().double(), W1.half().double(), W2.half().double()
                 hid16 = torch.relu(h16 @ W116.t() + b1.double()).half().double()
                 o64h = (h.double() + hid16 @ W216.t() + b2.double()) * sc.double() + sh.double()
                 assert (out.cpu().double() - o64h).abs().max() < 1e-3, (M, 'f16 feed-forward')
+                # kind::f16 fc: fp16 input copy and fp16 weights
+                hh16, Wh16 = h.half().cuda(), W.half().cuda()
+                ft16 = torch.empty(M, 128, device='cuda', dtype=torch.float16)
+                el.fill_(float('nan')); er.fill_(float('nan'))
+                _lib.check(lib.gnngls_fc_forward(_ops.DENSE_TCGEN05_F16, p(hh16), M, p(Wh16), p(alc), p(arc), p(ft16), _ops.FT_F16,
+                                                 p(el), p(er), _ops._stream()))
+                torch.cuda.synchronize()
+                f64 = h.half().double() @ W.half().double().t()
+                e64 = (f64.view(M, 8, 16) * al.double().view(1, 8, 16)).sum(-1)
+                r64 = (f64.view(M, 8, 16) * ar.double().view(1, 8, 16)).sum(-1)
+                assert (ft16.cpu().double() - f64).abs().max() < 5e-3, (M, 'f16 fc')
+                assert (el.cpu().double() - LOG2E * e64).abs().max() < 2e-4 and (er.cpu().double() - LOG2E * r64).abs().max() < 2e-4
 
 
 def test_glue_kernels_bit_exact():
@@ -316,7 +330,7 @@ def test_tf32_feature_storage_switch(monkeypatch):
     n, B = c.nB.tolist()
     y16 = run(m, n, B, c.x, 'tcgen05', 'kn')
     monkeypatch.setenv('GNNGLS_FT_DTYPE', 'tf32')
-    monkeypatch.setenv('GNNGLS_FF_DTYPE', 'tf32')
+    monkeypatch.setenv('GNNGLS_OP_DTYPE', 'tf32')
     y32 = run(m, n, B, c.x, 'tcgen05', 'kn')
     assert not np.array_equal(y16, y32)
     tol = tf32_budget(port, n, B, c.x, c.y64)
