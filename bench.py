@@ -349,7 +349,7 @@ def main():
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'tf32 (GNN contractions, fp32 accumulate) + fp64 (search)', 'data': 'synthetic',
+        'dtype': 'fp16 operands (10-bit mantissa, as TF32) with fp32 accumulate for the GNN contractions, fp32 elsewhere + fp64 (search)', 'data': 'synthetic',
         'config': dict(workload_config(args, world), weights=weights),
         'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu,
         'stage_ms_per_step': stage_ms, 'stage_coverage': round(total_stage / ms, 3) if ms else None,
