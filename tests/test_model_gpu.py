@@ -367,3 +367,35 @@ def test_split_star_pipeline_matches_fused(tmp_path):
         y = run(m, n, B, x, 'tcgen05', 'kn')
         assert np.isfinite(got['y%d' % n]).all()
         assert np.abs(got['y%d' % n] - y).max() <= 1e-5 * np.abs(y).max(), n
+
+
+@pytest.mark.parametrize('n', [150, 200, 380])
+def test_large_n_star_kernel_matches_csr_kernel(n):
+    """Above the sizes the CPU oracle handles in seconds: the fp16 K_n star kernel (opt-in shared memory > 48 KB, one or
+    two CTAs per SM) against the independent fp32 CSR kernel on the same inputs (fp16-representable features)."""
+    from gnngls_b200 import _lib
+    lib = _lib.load()
+    p = _ops._ptr
+    g = torch.Generator().manual_seed(n)
+    B = 1
+    N = n * (n - 1) // 2
+    M = B * N
+    ft = (torch.randn(M, 128, generator=g) * 2).half()
+    el, er = torch.randn(M, 8, generator=g) * 3, torch.randn(M, 8, generator=g) * 3
+    h = torch.randn(M, 128, generator=g)
+    sc, sh = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1
+    G = graph.LineGraph.complete(n, B, 'cuda')
+    indptr, indices = G.csr()
+    ftc, elc, erc, hc, scc, shc = ft.cuda(), el.cuda(), er.cuda(), h.cuda(), sc.cuda(), sh.cuda()
+    ft32 = ftc.float()
+    ref = torch.full((M, 128), float('nan'), device='cuda')
+    _lib.check(lib.gnngls_gat_aggregate_csr(p(indptr), p(indices), M, p(ft32), _ops.FT_F32, p(elc), p(erc), p(hc), None,
+                                            p(scc), p(shc), p(ref), None, _ops._stream()))
+    nbytes = lib.gnngls_gat_kn_workspace_bytes(B, n)
+    wk = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+    out = torch.full((M, 128), float('nan'), device='cuda')
+    _lib.check(lib.gnngls_gat_aggregate_kn(B, n, p(ftc), _ops.FT_F16, p(elc), p(erc), p(hc), None, p(scc), p(shc), p(out),
+                                           None, p(wk), nbytes, _ops._stream()))
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    assert np.isfinite(err) and err < 2e-3 * float(ft.abs().max()), (n, err)
