@@ -369,7 +369,7 @@ def test_split_star_pipeline_matches_fused(tmp_path):
         assert np.abs(got['y%d' % n] - y).max() <= 1e-5 * np.abs(y).max(), n
 
 
-@pytest.mark.parametrize('n', [150, 200, 380])
+@pytest.mark.parametrize('n', [150, 200, 380, 500, 560])
 def test_large_n_star_kernel_matches_csr_kernel(n):
     """Above the sizes the CPU oracle handles in seconds: the fp16 K_n star kernel (opt-in shared memory > 48 KB, one or
     two CTAs per SM) against the independent fp32 CSR kernel on the same inputs (fp16-representable features)."""
