@@ -702,7 +702,8 @@ __device__ __forceinline__ void star_f16_body(int n, const __half *__restrict__ 
         ELt[0 * KE + k] = a.x; ELt[1 * KE + k] = a.y; ELt[2 * KE + k] = a.z; ELt[3 * KE + k] = a.w;
         ELt[4 * KE + k] = c4.x; ELt[5 * KE + k] = c4.y; ELt[6 * KE + k] = c4.z; ELt[7 * KE + k] = c4.w;
     }
-    __syncthreads();                                          // el is in place; the feature rows and er are still in flight
+    cp_async_wait_all();
+    __syncthreads();
 
     {   // per-head top-2 of el over the star (warp w <-> head w)
         Top2 t2{-INFINITY, -INFINITY, -1};
@@ -736,8 +737,7 @@ __device__ __forceinline__ void star_f16_body(int n, const __half *__restrict__ 
             const float d = ELt[warp * KE + k] - t2.m1;
             EA[warp * KE + k] = make_float2(ex2(d), ex2(kSlope * d));
         }
-        cp_async_wait_all();                                                  // the top-2 / factor pass above ran under the
-        __syncthreads();                                                      // latency of the star's feature rows
+        __syncwarp();
         const uint32_t fh = (uint32_t)__cvta_generic_to_shared(Fh);
         const int q = lane >> 3, r = lane & 7;
         c.b4_addr = fh + (uint32_t)(((r + 8 * (q & 1)) * FH_LD + warp * 16 + 8 * (q >> 1)) * 2);
