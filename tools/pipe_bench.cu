@@ -14,6 +14,10 @@ __global__ void k(float *out, long long *cyc, float seed) {
 #pragma unroll
     for (int u = 0; u < U; ++u) { x[u] = seed + threadIdx.x * 1e-3f + u; p[u] = threadIdx.x + u; }
     float c[4][4] = {};
+    unsigned long long q2[U], c2;                       // packed fp32 pairs
+#pragma unroll
+    for (int u = 0; u < U; ++u) asm volatile("mov.b64 %0, {%1, %2};" : "=l"(q2[u]) : "f"(x[u]), "f"(x[u] + 1.f));
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(seed));
     __syncthreads();
     const long long t0 = clock64();
     for (int it = 0; it < ITERS; ++it) {
@@ -37,6 +41,8 @@ __global__ void k(float *out, long long *cyc, float seed) {
             if (OP == 13) asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(p[u]));
             if (OP == 14) asm volatile("max.f16x2 %0, %0, %1;" : "+r"(p[u]) : "r"(p[(u + 1) % U]));
             if (OP == 15) asm volatile("fma.rn.f16x2 %0, %0, %1, %1;" : "+r"(p[u]) : "r"(p[(u + 1) % U]));
+            if (OP == 16) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(q2[u]) : "l"(c2));
+            if (OP == 17) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(q2[u]) : "l"(c2));
         }
         if (OP >= 7) {
             // one tile-step of the star main loop: 8 weights = max(el+c1, 0.2*el+c2) -> ex2 -> pack -> 3 HMMA
@@ -67,7 +73,7 @@ __global__ void k(float *out, long long *cyc, float seed) {
     const long long t1 = clock64();
     float s = 0.f;
 #pragma unroll
-    for (int u = 0; u < U; ++u) s += x[u] + __uint_as_float(p[u]);
+    for (int u = 0; u < U; ++u) s += x[u] + __uint_as_float(p[u]) + (float)(q2[u] & 0xffff);
     for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) s += c[a][b];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
@@ -92,7 +98,7 @@ int main() {
     for (int w : {8, 32}) {
         run<0>("MUFU.EX2", w); run<1>("FMNMX", w); run<2>("FFMA", w); run<6>("FADD", w); run<3>("F2FP.PACK_AB", w);
         run<4>("HMMA.16816.F32", w); run<5>("HMMA.1688.TF32", w);
-        run<12>("EX2.f16x2", w); run<13>("TANH.f16x2", w); run<14>("HMNMX2", w); run<15>("HFMA2", w);
+        run<12>("EX2.f16x2", w); run<13>("TANH.f16x2", w); run<14>("HMNMX2", w); run<15>("HFMA2", w); run<16>("FMUL2 (f32x2)", w); run<17>("FFMA2 (f32x2)", w);
     }
     return 0;
 }
