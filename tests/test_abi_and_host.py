@@ -144,3 +144,27 @@ def test_synthetic_instances_are_reproducible():
     assert np.array_equal(D, D2) and np.array_equal(D, D.transpose(0, 2, 1)) and (np.diagonal(D, axis1=1, axis2=2) == 0).all()
     x = instances.edge_features(D)
     assert x.shape == (3, 45) and x.dtype == np.float32 and x[0, 0] == np.float32(D[0, 0, 1])
+
+
+def test_python_constants_match_header_enums():
+    """The ctypes side passes these as plain ints: they must be the values include/gnngls_b200.h declares."""
+    import os
+    import re
+    from gnngls_b200 import _ops
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'gnngls_b200.h')).read()
+    enums = {m.group(1): int(m.group(2)) for m in re.finditer(r'\b(GNNGLS_[A-Z0-9_]+)\s*=\s*(-?\d+)', hdr)}
+    assert enums['GNNGLS_FT_F32'] == _ops.FT_F32 and enums['GNNGLS_FT_TF32'] == _ops.FT_TF32 and enums['GNNGLS_FT_F16'] == _ops.FT_F16
+    assert enums['GNNGLS_DENSE_TCGEN05'] == _ops.DENSE_TCGEN05 and enums['GNNGLS_DENSE_SIMT'] == _ops.DENSE_SIMT
+    assert enums['GNNGLS_DENSE_TCGEN05_F16'] == _ops.DENSE_TCGEN05_F16
+
+
+def test_operand_dtype_switches(monkeypatch):
+    from gnngls_b200 import models
+    monkeypatch.delenv('GNNGLS_OP_DTYPE', raising=False)
+    monkeypatch.delenv('GNNGLS_FF_DTYPE', raising=False)
+    assert models._op_f16()
+    monkeypatch.setenv('GNNGLS_OP_DTYPE', 'tf32')
+    assert not models._op_f16()
+    monkeypatch.setenv('GNNGLS_OP_DTYPE', 'f16')
+    monkeypatch.setenv('GNNGLS_FF_DTYPE', 'TF32')
+    assert not models._op_f16()
