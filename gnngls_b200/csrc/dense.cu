@@ -598,7 +598,7 @@ constexpr int FF_WSTAGE_BYTES = 16384;                 // half of W1c: 2 boxes [
 constexpr int FF_A_BYTES = BM * D_ * 4;                // 64 KB: 4 boxes [128 x 32]
 constexpr int FF_SVEC = 4 * D_ + HID_;                 // b2 | bn_scale | bn_shift | b1 | b2*bn_scale + bn_shift
 constexpr int FF_THREADS = 15 * 32;                    // warp0 W-TMA, warp1 MMA, warps 2..9 epilogue-1, warp10 A-TMA, warps 11..14 A staging + final epilogue
-constexpr int FF_NBARS = 4 + 2 * FF_WSTAGES + 8 + 4;
+constexpr int FF_NBARS = 4 + 2 * FF_WSTAGES + 8 + 4 + 16;
 constexpr int FF_THREADS_F16 = 19 * 32;                // fp16 variant: + warps 15..18, final epilogue only
 constexpr int FF_TMEM_COLS = 512;
 constexpr size_t ff_smem_bytes(bool f16) {
@@ -676,7 +676,10 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t *d1_full = w_empty + FF_WSTAGES, *h_full = d1_full + 2, *d2_full = h_full + 2, *d2_empty = d2_full + 2;
     uint64_t *a_full2 = d2_empty + 2, *a_empty2 = d2_empty + 3;      // second A buffer in shared memory (fp16 variant)
     uint64_t *at_full2 = d2_empty + 4, *at_empty2 = d2_empty + 5;    // second A buffer in tensor memory (fp16 variant)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 6);
+    // fp16 variant: the A buffers are handed over per 32-column k-block [buffer][kb], so the next tile's TMA boxes start
+    // landing as soon as the final epilogue has finished with the corresponding output chunk
+    uint64_t *ak_full = d2_empty + 6, *ak_empty = d2_empty + 14;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 22);
     constexpr int NTHREADS = F16 ? FF_THREADS_F16 : FF_THREADS;
     const bool skip_smem = F16 && p.skip_is_a;                       // the staged operand IS the fp32 skip tensor
 
@@ -699,6 +702,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         constexpr int FE_WARPS = F16 ? 8 : 4;                 // warps that share a tile's final epilogue
         mbar_init(a_full, 1); mbar_init(a_empty, F16 ? FE_WARPS : 4); mbar_init(at_full, 4); mbar_init(at_empty, 1);
         mbar_init(a_full2, 1); mbar_init(a_empty2, FE_WARPS); mbar_init(at_full2, 4); mbar_init(at_empty2, 1);
+        for (int s2 = 0; s2 < 8; ++s2) { mbar_init(&ak_full[s2], 1); mbar_init(&ak_empty[s2], 4); }
         for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
         for (int g = 0; g < 2; ++g) {
             mbar_init(&d1_full[g], 1); mbar_init(&h_full[g], EPI_WARPS);
@@ -720,6 +724,15 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             uint32_t it = 0;
             for (int64_t w = tile0; w < m_tiles; w += tile_step, ++it) {
                 const uint32_t ab = F16 ? (it & 1) : 0, an = F16 ? (it >> 1) : it;     // buffer, use count of that buffer
+                if (F16) {
+                    for (int o = 0; o < 4; ++o) {
+                        const int kb = ((o & 1) << 1) | (o >> 1);    // 0, 2, 1, 3: the order the final epilogue frees them
+                        mbar_wait(&ak_empty[ab * 4 + kb], (an & 1) ^ 1);
+                        mbar_expect_tx(&ak_full[ab * 4 + kb], BM * BK * 4);
+                        tma_load_2d(&tmA, &ak_full[ab * 4 + kb], sA + ab * FF_A_BYTES + kb * (BM * BK * 4), kb * BK, (int)w * BM);
+                    }
+                    continue;
+                }
                 uint64_t *af = ab ? a_full2 : a_full, *ae = ab ? a_empty2 : a_empty;
                 mbar_wait(ae, (an & 1) ^ 1);                  // the previous user of this buffer is done with it
                 mbar_expect_tx(af, FF_A_BYTES);
@@ -761,17 +774,15 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     __syncwarp();
                     stg_store_tile(blk, p.out, p.out_tf32, w * BM + q * 32, c2 * 32, D_, p.M, lane, p.out_op_f16);
                     __syncwarp();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our smem accesses before the next TMA box lands here
+                    if (lane == 0) mbar_arrive(&ak_empty[(t & 1) * 4 + c2]);         // k-block c2 of this tile's A buffer is free
                 } else {
                     epilogue_tile32<EPI_FF2>(p, svec, stg, w * BM + q * 32, c2 * 32, v, lane);
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (F16) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our smem writes before the next TMA into this buffer
-            if (lane == 0) {
-                mbar_arrive(&d2_empty[d]);
-                if (F16) mbar_arrive((t & 1) ? a_empty2 : a_empty);   // this tile's A buffer may be overwritten now
-            }
+            if (lane == 0) mbar_arrive(&d2_empty[d]);
         };
         if (F16 && warp >= 15) {
             // ---- fp16 variant: warps 15..18 take output columns [0,64) of every tile's final epilogue; the staging
@@ -783,11 +794,13 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int64_t w_prev = -1;
         for (int64_t w = tile0; w < m_tiles; w += tile_step, ++it) {
             const uint32_t ab = F16 ? (it & 1) : 0, an = F16 ? (it >> 1) : it;
-            mbar_wait(ab ? a_full2 : a_full, an & 1);
+            if (!F16) mbar_wait(a_full, an & 1);
             mbar_wait(ab ? at_empty2 : at_empty, (an & 1) ^ 1);   // GEMM1 of the previous user has finished reading this A[tmem]
             tc_fence_after();
 #pragma unroll 1
-            for (int kb = 0; kb < D_ / BK; ++kb) {
+            for (int o = 0; o < D_ / BK; ++o) {
+                const int kb = F16 ? (((o & 1) << 1) | (o >> 1)) : o;
+                if (F16) mbar_wait(&ak_full[ab * 4 + kb], an & 1);
                 float v[32];
                 const unsigned char *row = sA + ab * FF_A_BYTES + kb * (BM * BK * 4) + r * 128;
 #pragma unroll
