@@ -124,12 +124,32 @@ class RegretGLS:
         tours = torch.empty(B, n + 1, dtype=torch.int32).pin_memory()
         costs = torch.empty(B, dtype=torch.float64).pin_memory()
         dev = next(self.model.parameters()).device
-        for b0 in range(0, B, chunk):
-            b1 = min(B, b0 + chunk)
-            src = D_host[b0:b1]
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, '_copy_stream', None) is None or self._copy_stream.device != dev:
+            self._copy_stream = torch.cuda.Stream(dev)
+        copy_stream = self._copy_stream
+        starts = list(range(0, B, chunk))
+
+        def upload(b0):
+            """Host->device copy of one chunk on the copy stream (double-buffered: the next chunk's distance
+            matrices travel over PCIe while the current chunk is being solved)."""
+            src = D_host[b0:min(B, b0 + chunk)]
             if not src.is_pinned():
                 src = src.contiguous().pin_memory()
-            Dd = src.to(dev, non_blocking=True)
+            with torch.cuda.stream(copy_stream):
+                Dd = src.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return Dd, ev
+
+        nxt = upload(starts[0]) if starts else None
+        for idx, b0 in enumerate(starts):
+            b1 = min(B, b0 + chunk)
+            Dd, ev = nxt
+            if idx + 1 < len(starts):
+                nxt = upload(starts[idx + 1])
+            main.wait_event(ev)
+            Dd.record_stream(main)                # allocated on the copy stream, consumed on the compute stream
             res = self.solve(Dd, **kw)
             tours[b0:b1].copy_(res.best_tours, non_blocking=True)
             costs[b0:b1].copy_(res.best_costs, non_blocking=True)
