@@ -56,8 +56,7 @@ KERNELS_PER_CALL = {
     'gnngls_moves_eval_a2a': 1, 'gnngls_moves_eval_o2a': 1, 'gnngls_local_search_batch': 1, 'gnngls_gls_batch': 1,
     'gnngls_nn_init_batch': 1, 'gnngls_tour_cost_batch': 1, 'gnngls_edge_features': 1, 'gnngls_embed_forward': 1,
     'gnngls_fc_forward': 1, 'gnngls_gat_aggregate_csr': 1,
-    # fused star kernel, or star + concurrently running combine kernel with GNNGLS_STAR_PIPELINE=split
-    'gnngls_gat_aggregate_kn': 2 if os.environ.get('GNNGLS_STAR_PIPELINE', '').lower().startswith('s') else 1,
+    'gnngls_gat_aggregate_kn': 1,
     # one fused tcgen05 kernel; the SIMT debug path (impl == 1, first argument) runs two GEMM kernels
     'gnngls_ff_forward': lambda args: 2 if args[0] == 1 else 1,
     'gnngls_decision_forward': 1, 'gnngls_regret_postprocess': 1,

@@ -25,6 +25,7 @@ SOURCES = {
     'search.cu': ['-fmad=false'],
     'glue.cu': ['-fmad=false'],
     'gat.cu': [],
+    'gat_kn.cu': [],
     'dense.cu': [],
 }
 

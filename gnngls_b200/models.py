@@ -92,7 +92,7 @@ def tf32_round(t):
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-_KN_MAX_N_F16, _KN_MAX_N_F32 = 560, 380
+_KN_MAX_N = 1024      # largest vertex star the K_n kernel holds in one CTA's shared memory (csrc/gat_kn.cu)
 
 
 def _op_f16():
@@ -144,9 +144,7 @@ def _gat_block(G, h_op, skip, Wfc, al, ar, bias, bn_scale, bn_shift, dense_impl,
     p = _ops._ptr
     with stage('fc'):
         _lib.check(lib.gnngls_fc_forward(dense_impl, p(h_op), M, p(Wfc), p(al), p(ar), p(ft), ft_dtype, p(el), p(er), st))
-    # a vertex star must fit one CTA's shared memory: n <= 560 with fp16 features, n <= 380 with fp32 storage
-    use_kn = gat_impl == 'kn' or (gat_impl == 'auto' and G.kind == 'kn'
-                                  and G.n <= (_KN_MAX_N_F16 if ft_dtype == _ops.FT_F16 else _KN_MAX_N_F32))
+    use_kn = gat_impl == 'kn' or (gat_impl == 'auto' and G.kind == 'kn' and G.n <= _KN_MAX_N)
     if use_kn:
         if G.kind != 'kn':
             raise ValueError("gat_impl='kn' needs a LineGraph.complete graph")

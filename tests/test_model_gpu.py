@@ -3,9 +3,9 @@ models.py outputs (golden, fp64 yardstick) and the torch oracle.
 
 Tolerances on the raw model output (|y| ~ 30 for the seeded random-init weights), yardstick = the
 reference's own models.py evaluated in fp64 (golden `y64`):
-  fp32 path  (SIMT dense + CSR aggregate): max|y - y64| <= 1e-5 * max|y64|
-             (the fp32 torch oracle itself is within 2e-6 * max|y64| of fp64);
-  TF32 paths (tcgen05 dense and/or mma.sync K_n aggregate): max|y - y64| <= 2 * E_tf32 + 1e-4 * max|y64|,
+  fp32 path  (SIMT dense + CSR or K_n aggregate, both fp32 arithmetic): max|y - y64| <= 1e-5 * max|y64| (CSR),
+             2e-5 * max|y64| (K_n sorted-prefix kernel); the fp32 torch oracle itself is within 2e-6 * max|y64| of fp64;
+  TF32 paths (tcgen05 dense contractions, fp16/TF32 operands): max|y - y64| <= 2 * E_tf32 + 1e-4 * max|y64|,
              where E_tf32 is the error of the SAME oracle evaluated with TF32-rounded GEMM operands
              (what torch 1.11's default allow_tf32 computes on Ampere+; oracle.model_port.emulate_tf32),
              measured per case at test time (E_tf32 ~ 1.2e-2 .. 2.2e-2 here, i.e. ~5e-4 relative).
@@ -61,7 +61,10 @@ def test_model_matches_reference_golden(dense, gat):
         n, B = c.nB.tolist()
         y = run(m, n, B, c.x, dense, gat)
         err = np.abs(y - c.y64).max()
-        tol = REL_FP32 * np.abs(c.y64).max() if (dense, gat) == ('simt', 'csr') else tf32_budget(port, n, B, c.x, c.y64)
+        if dense == 'simt':
+            tol = (REL_FP32 if gat == 'csr' else 2 * REL_FP32) * np.abs(c.y64).max()
+        else:
+            tol = tf32_budget(port, n, B, c.x, c.y64)
         print(f'{dense}+{gat} n={n} B={B}: max|y-y64|={err:.3e} tol={tol:.3e} (|y|max={np.abs(c.y64).max():.3f})')
         assert y.shape == c.y64.shape and np.isfinite(y).all()
         assert err <= tol, (dense, gat, n, err)
@@ -82,7 +85,7 @@ def test_paths_agree_and_batching_is_transparent():
     port.float()
     assert np.abs(ref - y64).max() < REL_FP32 * np.abs(y64).max()
     tol = tf32_budget(port, n, B, x, y64)
-    assert np.abs(run(m, n, B, x, 'simt', 'kn') - y64).max() < tol
+    assert np.abs(run(m, n, B, x, 'simt', 'kn') - y64).max() < 2 * REL_FP32 * np.abs(y64).max()
     assert np.abs(run(m, n, B, x, 'tcgen05', 'kn') - y64).max() < tol
     yk = run(m, n, B, x, 'tcgen05', 'kn')
     for b in range(B):          # TF32 path: batching is transparent too (bitwise)
@@ -233,7 +236,7 @@ def test_pipeline_tours_bit_exact_given_gpu_regrets():
 @pytest.mark.parametrize('n,B', [(3, 4), (4, 3), (7, 2), (33, 2), (100, 1)])
 def test_model_sizes_vs_fp64_oracle(n, B):
     """Smallest legal graphs (n=3: every node has 2 in-edges), odd sizes that exercise every padding path of the
-    star kernel (n not a multiple of 8/16) and one full-size TSP100 instance."""
+    K_n kernel (n not a multiple of 4/8/16) and one full-size TSP100 instance."""
     port, m = make_models()
     _, D = instances.random_instances(B, n, seed=100 + n)
     x = (instances.edge_features(D) / np.float32(np.sqrt(2))).reshape(-1, 1)
@@ -273,7 +276,7 @@ def test_public_layer_and_gatconv_forward():
 def test_aggregate_kernels_all_storage_formats(n, B):
     """gnngls_gat_aggregate_kn / _csr with fp32, TF32 and fp16 feature storage against an fp64 evaluation of the same
     softmax-aggregate on inputs that are exactly representable in fp16 (so only the attention weights round).
-    Sizes straddle the 8/16-member k-step and 16/32-destination tile boundaries of the tensor-core kernels."""
+    Sizes straddle the chunk boundaries of the K_n kernel's scans and both of its sort capacities (64, 128 slots)."""
     from gnngls_b200 import _lib
     lib = _lib.load()
     p = _ops._ptr
@@ -282,7 +285,7 @@ def test_aggregate_kernels_all_storage_formats(n, B):
     M = B * N
     ft = (torch.randn(M, 128, generator=g) * 2).half().float()
     el, er = torch.randn(M, 8, generator=g) * 3, torch.randn(M, 8, generator=g) * 3       # log2-domain scores
-    # a few dominant sources (far above every other member of their stars): the fp16 star kernel then takes its
+    # a few dominant sources (far above every other member of their stars): the K_n kernel then takes its
     # exact-row path for the destination that is itself the arg-max member
     hot = torch.randint(0, M, (max(1, M // 7),), generator=g)
     el[hot, torch.randint(0, 8, (len(hot),), generator=g)] += 25.0
@@ -317,7 +320,7 @@ def test_aggregate_kernels_all_storage_formats(n, B):
             else:
                 _lib.check(lib.gnngls_gat_aggregate_kn(B, n, p(ftc), ft_dtype, p(elc), p(erc), p(hc), p(bc), p(scc),
                                                        p(shc), p(out), None, p(wk), nbytes, _ops._stream()))
-                tol = 2e-3 * scale                    # 10-bit attention weights (truncated TF32 / rounded fp16)
+                tol = 3e-5 * scale                    # sorted-prefix formulation: fp32 arithmetic throughout
             torch.cuda.synchronize()
             err = (out.cpu().double() - ref).abs().max().item()
             assert np.isfinite(err) and err < tol, (n, B, ft_dtype, kind, err, tol)
@@ -337,65 +340,40 @@ def test_tf32_feature_storage_switch(monkeypatch):
     assert np.abs(y32 - c.y64).max() <= tol and np.abs(y16 - c.y64).max() <= tol
 
 
-def test_split_star_pipeline_matches_fused(tmp_path):
-    """GNNGLS_STAR_PIPELINE=split (star kernel + concurrently running combine kernel, read once per process, hence
-    the subprocess) computes the same merge as the default fused kernel."""
-    import os
-    import subprocess
-    import sys
-    port, m = make_models()
-    cases = [(12, 5, 4), (33, 3, 5), (100, 2, 6)]
-    script = tmp_path / 'split_run.py'
-    script.write_text(
-        "import sys, numpy as np, torch\n"
-        "sys.path.insert(0, %r)\n"
-        "from tests.test_model_gpu import make_models, run\n"
-        "from gnngls_b200 import instances\n"
-        "port, m = make_models()\n"
-        "out = {}\n"
-        "for n, B, seed in %r:\n"
-        "    _, D = instances.random_instances(B, n, seed=seed)\n"
-        "    x = (instances.edge_features(D) / np.float32(np.sqrt(2))).reshape(-1, 1)\n"
-        "    out['y%%d' %% n] = run(m, n, B, x, 'tcgen05', 'kn')\n"
-        "np.savez(%r, **out)\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), cases, str(tmp_path / 'split.npz')))
-    env = dict(os.environ, GNNGLS_STAR_PIPELINE='split')
-    subprocess.run([sys.executable, str(script)], check=True, env=env, timeout=300)
-    got = np.load(tmp_path / 'split.npz')
-    for n, B, seed in cases:
-        _, D = instances.random_instances(B, n, seed=seed)
-        x = (instances.edge_features(D) / np.float32(np.sqrt(2))).reshape(-1, 1)
-        y = run(m, n, B, x, 'tcgen05', 'kn')
-        assert np.isfinite(got['y%d' % n]).all()
-        assert np.abs(got['y%d' % n] - y).max() <= 1e-5 * np.abs(y).max(), n
-
-
-@pytest.mark.parametrize('n', [150, 200, 380, 500, 560])
-def test_large_n_star_kernel_matches_csr_kernel(n):
-    """Above the sizes the CPU oracle handles in seconds: the fp16 K_n star kernel (opt-in shared memory > 48 KB, one or
-    two CTAs per SM) against the independent fp32 CSR kernel on the same inputs (fp16-representable features)."""
+@pytest.mark.parametrize('n,ft_dtype', [(128, 'f16'), (129, 'f16'), (150, 'f32'), (200, 'f16'), (256, 'f16'), (257, 'f32'),
+                                        (380, 'f16'), (500, 'f16'), (512, 'f32'), (513, 'f16'), (700, 'f16'), (1000, 'f16')])
+def test_large_n_kn_kernel_vs_fp64_rows(n, ft_dtype):
+    """Above the sizes the torch oracle handles in seconds (every shared-memory configuration of csrc/gat_kn.cu: 4, 2
+    and 1 heads per CTA, 4..32 sort elements per lane): 400 sampled destination rows against an fp64 evaluation with
+    arithmetic adjacency (tests/_kn_ref.py).  Features are fp16-representable, so only fp32 arithmetic separates them."""
     from gnngls_b200 import _lib
+    from tests import _kn_ref
     lib = _lib.load()
     p = _ops._ptr
     g = torch.Generator().manual_seed(n)
-    B = 1
+    B = 2 if n <= 257 else 1
     N = n * (n - 1) // 2
     M = B * N
     ft = (torch.randn(M, 128, generator=g) * 2).half()
     el, er = torch.randn(M, 8, generator=g) * 3, torch.randn(M, 8, generator=g) * 3
+    hot = torch.randint(0, M, (max(1, M // 50),), generator=g)          # dominant members: exercises the exact arg-max row
+    el[hot, torch.randint(0, 8, (len(hot),), generator=g)] += 30.0
     h = torch.randn(M, 128, generator=g)
+    bias = torch.randn(128, generator=g) * 0.1
     sc, sh = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1
-    G = graph.LineGraph.complete(n, B, 'cuda')
-    indptr, indices = G.csr()
-    ftc, elc, erc, hc, scc, shc = ft.cuda(), el.cuda(), er.cuda(), h.cuda(), sc.cuda(), sh.cuda()
-    ft32 = ftc.float()
-    ref = torch.full((M, 128), float('nan'), device='cuda')
-    _lib.check(lib.gnngls_gat_aggregate_csr(p(indptr), p(indices), M, p(ft32), _ops.FT_F32, p(elc), p(erc), p(hc), None,
-                                            p(scc), p(shc), p(ref), None, _ops._stream()))
+    f16 = ft_dtype == 'f16'
+    ftc = ft.cuda() if f16 else ft.float().cuda()
+    elc, erc, hc, bc, scc, shc = el.cuda(), er.cuda(), h.cuda(), bias.cuda(), sc.cuda(), sh.cuda()
     nbytes = lib.gnngls_gat_kn_workspace_bytes(B, n)
     wk = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
     out = torch.full((M, 128), float('nan'), device='cuda')
-    _lib.check(lib.gnngls_gat_aggregate_kn(B, n, p(ftc), _ops.FT_F16, p(elc), p(erc), p(hc), None, p(scc), p(shc), p(out),
-                                           None, p(wk), nbytes, _ops._stream()))
+    _lib.check(lib.gnngls_gat_aggregate_kn(B, n, p(ftc), _ops.FT_F16 if f16 else _ops.FT_F32, p(elc), p(erc), p(hc), p(bc),
+                                           p(scc), p(shc), p(out), None, p(wk), nbytes, _ops._stream()))
     torch.cuda.synchronize()
-    err = (out - ref).abs().max().item()
-    assert np.isfinite(err) and err < 2e-3 * float(ft.abs().max()), (n, err)
+    out = out.cpu()
+    assert torch.isfinite(out).all()
+    rng = np.random.default_rng(n)
+    rows = np.unique(np.concatenate([rng.integers(0, M, 380), hot[:20].numpy(), [0, N - 1, M - 1]]))
+    ref = _kn_ref.aggregate_rows(n, rows, ft.float().numpy(), el.numpy(), er.numpy(), h.numpy(), bias.numpy(), sc.numpy(), sh.numpy())
+    err = np.abs(out.numpy()[rows].astype(np.float64) - ref).max()
+    assert err < 3e-5 * float(ft.abs().max()), (n, err)

@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""GPU diagnostic for gnngls_gat_aggregate_kn (csrc/gat_kn.cu): every shared-memory configuration against the fp64
+row oracle of tests/_kn_ref.py, plus kernel time.  Prints one line per case; exit status 1 on any mismatch.
+
+    python tools/kn_check.py [--quick]
+"""
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, __file__.rsplit('/', 2)[0])
+from gnngls_b200 import _lib, _ops  # noqa: E402
+from tests import _kn_ref  # noqa: E402  (diagnostic script, not product code)
+
+
+def case(n, B, f16, seed=0, hot=True, ties=False, reps=0):
+    lib = _lib.load()
+    p = _ops._ptr
+    g = torch.Generator().manual_seed(1000 * n + B + seed)
+    N = n * (n - 1) // 2
+    M = B * N
+    ft = (torch.randn(M, 128, generator=g) * 2).half()
+    el, er = torch.randn(M, 8, generator=g) * 3, torch.randn(M, 8, generator=g) * 3
+    if ties:
+        el, er = el.round(), er.round()
+    if hot:
+        hs = torch.randint(0, M, (max(1, M // 9),), generator=g)
+        el[hs, torch.randint(0, 8, (len(hs),), generator=g)] += 25.0
+        el[hs[0]] += 60.0
+    h = torch.randn(M, 128, generator=g)
+    bias = torch.randn(128, generator=g) * 0.1
+    sc, sh = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1
+    ftc = ft.cuda() if f16 else ft.float().cuda()
+    elc, erc, hc, bc, scc, shc = el.cuda(), er.cuda(), h.cuda(), bias.cuda(), sc.cuda(), sh.cuda()
+    nbytes = lib.gnngls_gat_kn_workspace_bytes(B, n)
+    wk = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+    out = torch.full((M, 128), float('nan'), device='cuda')
+
+    def launch():
+        _lib.check(lib.gnngls_gat_aggregate_kn(B, n, p(ftc), _ops.FT_F16 if f16 else _ops.FT_F32, p(elc), p(erc), p(hc), p(bc),
+                                               p(scc), p(shc), p(out), None, p(wk), nbytes, _ops._stream()))
+    launch()
+    torch.cuda.synchronize()
+    ms = float('nan')
+    if reps:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            launch()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+    o = out.cpu().numpy()
+    rng = np.random.default_rng(n)
+    rows = np.unique(np.concatenate([rng.integers(0, M, 300 if n > 40 else min(M, 600)), [0, N - 1, M - 1]]))
+    if n <= 40:
+        rows = np.arange(M) if M <= 4000 else rows
+    ref = _kn_ref.aggregate_rows(n, rows, ft.float().numpy(), el.numpy(), er.numpy(), h.numpy(), bias.numpy(), sc.numpy(), sh.numpy())
+    bad = ~np.isfinite(o[rows])
+    err = np.abs(np.where(bad, 0, o[rows]).astype(np.float64) - ref)
+    worst = np.unravel_index(err.argmax(), err.shape)
+    scale = float(ft.abs().max())
+    ok = (not bad.any()) and err.max() < 3e-5 * scale
+    print(f'n={n:5d} B={B:4d} {"f16" if f16 else "f32"} hot={int(hot)} ties={int(ties)}: max err {err.max():.3e} (tol {3e-5 * scale:.1e}) '
+          f'nan={int(bad.sum())} worst row {rows[worst[0]]} (local {rows[worst[0]] % N}) col {worst[1]}  {ms:8.3f} ms  {"ok" if ok else "FAIL"}',
+          flush=True)
+    return ok
+
+
+def main():
+    quick = '--quick' in sys.argv
+    ok = True
+    t0 = time.time()
+    sizes = [3, 4, 5, 8, 9, 16, 17, 20, 33, 50, 64, 65, 100, 128]
+    if not quick:
+        sizes += [129, 200, 256, 257, 500]
+    for n in sizes:
+        for f16 in (True, False):
+            B = 3 if n <= 128 else 1
+            ok &= case(n, B, f16)
+    ok &= case(20, 7, True, ties=True)
+    ok &= case(100, 2, True, ties=True)
+    ok &= case(100, 2, True, hot=False)
+    if not quick:
+        ok &= case(1000, 1, True)
+        ok &= case(100, 256, True, hot=False, reps=20)
+        ok &= case(50, 1024, True, hot=False, reps=20)
+        ok &= case(20, 4096, True, hot=False, reps=20)
+    print('kn_check', 'PASSED' if ok else 'FAILED', f'{time.time() - t0:.0f}s')
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == '__main__':
+    main()
