@@ -26,6 +26,7 @@ SOURCES = {
     'glue.cu': ['-fmad=false'],
     'gat.cu': [],
     'gat_kn.cu': [],
+    'gat_kn_tc.cu': [],
     'dense.cu': [],
 }
 

@@ -38,82 +38,9 @@
 //      dispatched earlier: blockIdx order), merges in fixed (lower, higher) order -- deterministic and
 //      batching-invariant bitwise -- applies bias + skip + BN1 and writes h1.  The consumed records are
 //      discarded from L2 so that they never travel to HBM.
-#include <cuda_fp16.h>
-#include <cstdint>
-#include <cstdlib>
-#include <cmath>
-#include "common.h"
+#include "gat_kn.cuh"
 
 namespace {
-
-constexpr int D_ = GNNGLS_EMBED_DIM;   // 128
-constexpr int H_ = GNNGLS_HEADS;       // 8
-constexpr int F_ = GNNGLS_HEAD_DIM;    // 16
-constexpr float kSlope = 0.2f;
-constexpr float kFixFrac = 0.9f;       // self weight / row total above which the arg-max row is redone exactly
-
-__device__ __forceinline__ float ex2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float lrelu(float s) { return fmaxf(s, kSlope * s); }
-__device__ __forceinline__ uint32_t tf32_bits(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float4 tf32_round4(float4 v) {
-    return make_float4(__uint_as_float(tf32_bits(v.x)), __uint_as_float(tf32_bits(v.y)),
-                       __uint_as_float(tf32_bits(v.z)), __uint_as_float(tf32_bits(v.w)));
-}
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// the 128-byte line at `p` will not be read again: a dirty copy in L2 need not be written back
-__device__ __forceinline__ void discard_l2_128(const void *p) {
-    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(int *p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-template <int COUNT>
-__device__ __forceinline__ void group_barrier(int id) {
-    if (COUNT == 32) __syncwarp();
-    else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(COUNT) : "memory");
-}
-
-// line-graph node id of the TSP edge {a,b}, a != b (sorted-tuple order, datasets.py:56-60)
-__host__ __device__ __forceinline__ int kn_node(int a, int b, int n) {
-    const int i = a < b ? a : b, j = a < b ? b : a;
-    return i * (2 * n - i - 1) / 2 + (j - i - 1);
-}
-
-// 4 consecutive features from shared memory
-__device__ __forceinline__ float4 lds_ft4(const unsigned char *p, float) { return *reinterpret_cast<const float4 *>(p); }
-__device__ __forceinline__ float4 lds_ft4(const unsigned char *p, __half) {
-    const uint2 raw = *reinterpret_cast<const uint2 *>(p);
-    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
-    return make_float4(a.x, a.y, b.x, b.y);
-}
-
-struct KnArgs {
-    int n;
-    const void *ft;                       // [M,128] FT
-    const float *el, *er;                 // [M,8] log2 domain
-    float *recV;                          // [M,128] partial numerators of the lower star
-    float *recDM;                         // [M,8,2] (denominator, reference max) of the lower star
-    int *flags;                           // [B*n*HG] "star has published"
-    const float *h, *bias, *bn_scale, *bn_shift;
-    float *h1, *h1_tf32;
-};
 
 // Shared-memory layout.  Per head: the table region T_h (rows 0..m = prefix tables, row m+1 = exact arg-max row)
 // doubles as the home of the arrays that are dead before the scan starts (scores, sorted scores, ranks); the
@@ -646,6 +573,13 @@ extern "C" int gnngls_gat_aggregate_kn(int B, int n, const void *ft, int ft_dtyp
     args.h = h; args.bias = gat_bias; args.bn_scale = bn_scale; args.bn_shift = bn_shift;
     args.h1 = h1; args.h1_tf32 = h1_tf32;
     GNNGLS_CUDA_OK(cudaMemsetAsync(args.flags, 0, sizeof(int) * (size_t)B * n * H_, st));
+    // fp16 features, n <= 128: tcgen05 indicator-matrix kernel (gat_kn_tc.cu); otherwise, or with GNNGLS_KN_IMPL=scan,
+    // the exact fp32 sorted-prefix kernel of this file
+    static const bool force_scan = [] {
+        const char *e = getenv("GNNGLS_KN_IMPL");
+        return e && (e[0] == 's' || e[0] == 'S');
+    }();
+    if (ft_dtype == GNNGLS_FT_F16 && n <= 128 && !force_scan) return gnngls::launch_kn_tc(args, B, st);
     if (ft_dtype == GNNGLS_FT_F16) return launch_for_n<__half>(args, B, st);
     return launch_for_n<float>(args, B, st);
 }

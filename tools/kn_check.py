@@ -62,8 +62,11 @@ def case(n, B, f16, seed=0, hot=True, ties=False, reps=0):
     err = np.abs(np.where(bad, 0, o[rows]).astype(np.float64) - ref)
     worst = np.unravel_index(err.argmax(), err.shape)
     scale = float(ft.abs().max())
-    ok = (not bad.any()) and err.max() < 3e-5 * scale
-    print(f'n={n:5d} B={B:4d} {"f16" if f16 else "f32"} hot={int(hot)} ties={int(ties)}: max err {err.max():.3e} (tol {3e-5 * scale:.1e}) '
+    import os
+    tc = f16 and n <= 128 and not os.environ.get('GNNGLS_KN_IMPL', '').lower().startswith('s')
+    tol = (1.5e-3 if tc else 3e-5) * scale     # tcgen05 path: fp16 operands (weights x features rounded to fp16)
+    ok = (not bad.any()) and err.max() < tol
+    print(f'n={n:5d} B={B:4d} {"f16" if f16 else "f32"} hot={int(hot)} ties={int(ties)}: max err {err.max():.3e} rms {np.sqrt((err**2).mean()):.2e} (tol {tol:.1e}) '
           f'nan={int(bad.sum())} worst row {rows[worst[0]]} (local {rows[worst[0]] % N}) col {worst[1]}  {ms:8.3f} ms  {"ok" if ok else "FAIL"}',
           flush=True)
     return ok

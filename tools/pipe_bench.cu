@@ -41,10 +41,15 @@ __global__ void k(float *out, long long *cyc, float seed) {
             if (OP == 13) asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(p[u]));
             if (OP == 14) asm volatile("max.f16x2 %0, %0, %1;" : "+r"(p[u]) : "r"(p[(u + 1) % U]));
             if (OP == 15) asm volatile("fma.rn.f16x2 %0, %0, %1, %1;" : "+r"(p[u]) : "r"(p[(u + 1) % U]));
+            if (OP == 18) asm volatile("set.ge.f16x2.f16x2 %0, %0, %1;" : "+r"(p[u]) : "r"(p[(u + 1) % U]));
+            if (OP == 19) asm volatile("mul.rn.f16x2 %0, %0, %1;" : "+r"(p[u]) : "r"(p[(u + 1) % U]));
+            if (OP == 20) asm volatile("set.ge.f32.f32 %0, %0, %1;" : "+f"(x[u]) : "f"(seed));
+            if (OP == 21) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(p[u]) : "r"(p[(u + 1) % U]), "r"(p[(u + 2) % U]));
+            if (OP == 22) asm volatile("sub.u32 %0, %0, %1;" : "+r"(p[u]) : "r"(p[(u + 1) % U]));
             if (OP == 16) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(q2[u]) : "l"(c2));
             if (OP == 17) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(q2[u]) : "l"(c2));
         }
-        if (OP >= 7) {
+        if (OP >= 7 && OP <= 10) {
             // one tile-step of the star main loop: 8 weights = max(el+c1, 0.2*el+c2) -> ex2 -> pack -> 3 HMMA
             float w[U];
 #pragma unroll
@@ -99,6 +104,7 @@ int main() {
         run<0>("MUFU.EX2", w); run<1>("FMNMX", w); run<2>("FFMA", w); run<6>("FADD", w); run<3>("F2FP.PACK_AB", w);
         run<4>("HMMA.16816.F32", w); run<5>("HMMA.1688.TF32", w);
         run<12>("EX2.f16x2", w); run<13>("TANH.f16x2", w); run<14>("HMNMX2", w); run<15>("HFMA2", w); run<16>("FMUL2 (f32x2)", w); run<17>("FFMA2 (f32x2)", w);
+        run<18>("HSET2.BF.GE", w); run<19>("HMUL2", w); run<20>("FSET.BF.GE", w); run<21>("LOP3", w); run<22>("IADD", w);
     }
     return 0;
 }
