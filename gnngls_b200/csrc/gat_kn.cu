@@ -579,7 +579,9 @@ extern "C" int gnngls_gat_aggregate_kn(int B, int n, const void *ft, int ft_dtyp
         const char *e = getenv("GNNGLS_KN_IMPL");
         return e && (e[0] == 's' || e[0] == 'S');
     }();
-    if (ft_dtype == GNNGLS_FT_F16 && n <= 128 && !force_scan) return gnngls::launch_kn_tc(args, B, st);
+    // (its finalise-two-iterations-later schedule needs a grid of at least n CTAs, or a single wave)
+    const int sms = gnngls::device_sm_count();
+    if (ft_dtype == GNNGLS_FT_F16 && n <= 128 && !force_scan && (sms >= n || (int64_t)B * n <= sms)) return gnngls::launch_kn_tc(args, B, st);
     if (ft_dtype == GNNGLS_FT_F16) return launch_for_n<__half>(args, B, st);
     return launch_for_n<float>(args, B, st);
 }
