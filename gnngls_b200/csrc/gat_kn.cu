@@ -539,8 +539,10 @@ int launch_for_n(const KnArgs &args, int B, cudaStream_t st) {
 extern "C" size_t gnngls_gat_kn_workspace_bytes(int B, int n) {
     if (B <= 0 || n <= 0) return 0;
     const size_t M = (size_t)B * ((size_t)n * (n - 1) / 2);
-    // numerator records + (denominator, max) records + one flag per (star, head group)
-    return sizeof(float) * M * (D_ + 2 * H_) + sizeof(int) * (size_t)B * n * H_;
+    // numerator records + (denominator, max) records + one flag per (star, head group); the tcgen05 kernel keeps two records per node
+    const size_t scan = sizeof(float) * M * (D_ + 2 * H_) + sizeof(int) * (size_t)B * n * H_;
+    const size_t tc = n <= 128 ? gnngls::kn_tc_workspace_bytes(B, n) : 0;
+    return scan > tc ? scan : tc;
 }
 
 extern "C" int gnngls_gat_aggregate_kn(int B, int n, const void *ft, int ft_dtype, const float *el, const float *er,
@@ -572,16 +574,14 @@ extern "C" int gnngls_gat_aggregate_kn(int B, int n, const void *ft, int ft_dtyp
     args.flags = reinterpret_cast<int *>(args.recDM + M * 2 * H_);
     args.h = h; args.bias = gat_bias; args.bn_scale = bn_scale; args.bn_shift = bn_shift;
     args.h1 = h1; args.h1_tf32 = h1_tf32;
-    GNNGLS_CUDA_OK(cudaMemsetAsync(args.flags, 0, sizeof(int) * (size_t)B * n * H_, st));
     // fp16 features, n <= 128: tcgen05 indicator-matrix kernel (gat_kn_tc.cu); otherwise, or with GNNGLS_KN_IMPL=scan,
     // the exact fp32 sorted-prefix kernel of this file
     static const bool force_scan = [] {
         const char *e = getenv("GNNGLS_KN_IMPL");
         return e && (e[0] == 's' || e[0] == 'S');
     }();
-    // (its finalise-two-iterations-later schedule needs a grid of at least n CTAs, or a single wave)
-    const int sms = gnngls::device_sm_count();
-    if (ft_dtype == GNNGLS_FT_F16 && n <= 128 && !force_scan && (sms >= n || (int64_t)B * n <= sms)) return gnngls::launch_kn_tc(args, B, st);
+    if (ft_dtype == GNNGLS_FT_F16 && n <= 128 && !force_scan) return gnngls::launch_kn_tc(args, B, workspace, st);
+    GNNGLS_CUDA_OK(cudaMemsetAsync(args.flags, 0, sizeof(int) * (size_t)B * n * H_, st));
     if (ft_dtype == GNNGLS_FT_F16) return launch_for_n<__half>(args, B, st);
     return launch_for_n<float>(args, B, st);
 }

@@ -12,9 +12,9 @@ struct KnArgs {
     int n;
     const void *ft;                       // [M,128] FT
     const float *el, *er;                 // [M,8] log2 domain
-    float *recV;                          // [M,128] partial numerators of the lower star
-    float *recDM;                         // [M,8,2] (denominator, reference max) of the lower star
-    int *flags;                           // [B*n*HG] "star has published"
+    float *recV;                          // partial numerators: [M,128] of the lower star (gat_kn.cu) / [M,2,128] of both stars (gat_kn_tc.cu)
+    float *recDM;                         // (denominator, reference max) per head: [M,8,2] / [M,2,8,2]
+    int *flags;                           // [B*n*HG] "star has published" (gat_kn.cu) / [B] stars out per instance (gat_kn_tc.cu)
     const float *h, *bias, *bn_scale, *bn_shift;
     float *h1, *h1_tf32;
 };
@@ -86,6 +86,7 @@ using gnngls::KnArgs;
 }  // namespace
 
 namespace gnngls {
-// tcgen05 variant (fp16 features, n <= 128); defined in gat_kn_tc.cu
-int launch_kn_tc(const KnArgs &args, int B, cudaStream_t st);
+// tcgen05 variant (fp16 features, n <= 128); defined in gat_kn_tc.cu.  Lays out its own records in `workspace`.
+size_t kn_tc_workspace_bytes(int B, int n);
+int launch_kn_tc(const KnArgs &args, int B, void *workspace, cudaStream_t st);
 }  // namespace gnngls

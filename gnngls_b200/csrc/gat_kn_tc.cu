@@ -22,53 +22,29 @@
 // When the star's largest score leads the runner-up by more than 6 (log2 units) its member is taken out of the MMA
 // (ref = runner-up) and added in fp32, so the self-exclusion of its own row never cancels a dominant term.
 //
-// Persistent kernel, one CTA of 4 teams x 128 threads per SM; CTA c takes the stars (instance b, vertex i) number c, c + G,
-// c + 2G, ... (G = grid size).  Destination {i,j} belongs to two stars; the one that is "behind" on the circle of vertices
-// ((i - j) mod n < n/2) finalises it, the other one publishes its partial (numerators, denominator, reference max) to
-// the record buffer -- so every star finalises at most n/2 rows and keeps them in a shared-memory stash.  Per star:
-//   1. (thread = member k when building operands, = destination row j afterwards) each team walks 2 heads: operand rows
-//      + indicator -> MMA -> accumulators; the MMA of the second head runs under the epilogue of the first.  Rows this
-//      star does not finalise go straight to the record buffer; ONE flag per star is released at the end.
-//   2. the rows a star finalises are finished TWO iterations later, in the shadow of that iteration's first MMA: its partner
-//      stars (numbers within n of it, so at most one iteration younger as long as G >= n) published a whole iteration ago,
-//      so their flags are up, and their records were fetched by cp.async at the top of the iteration (skip rows: L2
-//      prefetch); one warp per row merges in fixed (lower vertex, higher vertex) order -- deterministic and
-//      batching-invariant bitwise -- applies bias + skip + BN1 and writes h1 with full lines.
-// Nothing waits for global memory between the top of an iteration and its end.  A partner that is late all the same is
-// never waited for before this CTA's own star of the iteration is published: blocking waits (end of the iteration) then
-// only ever depend on stars of strictly older iterations, so they cannot form a cycle.
+// Persistent kernel, 128 threads per CTA (thread = member k when building operands, = destination row j afterwards), four
+// CTAs per SM, each with its own 128 tensor-memory columns; CTA c takes the stars (instance b, vertex i) number c, c + G, ...
+// Destination {i,j} belongs to two stars.  Each star writes its partial (16 numerators, denominator, reference max per
+// head) for every row to the record buffer -- slot 0 if it is the star of the lower vertex, slot 1 otherwise -- and
+// nothing in a star's work depends on any other star.  An instance whose n stars are all out (a counter per instance)
+// is merged D instances later, a slice of (n-1)/2 consecutive nodes per star slot: the two records are combined in fixed
+// (lower, higher) order -- deterministic and batching-invariant bitwise -- bias + skip + BN1 are applied and h1 is written
+// with full lines; the consumed records are dropped from L2 so they never travel to HBM.  The merge rows of a CTA are
+// spread over the shadows of its eight MMA chains (one per head), the only places where its warps would otherwise wait.
 #include "gat_kn.cuh"
-
-// Phase timing (debug builds only: -DKN_STAMPS): thread 0 of every team accumulates clock64() differences per phase;
-// read back with gnngls_debug_kn_stamps().
-#ifdef KN_STAMPS
-__device__ unsigned long long g_kn_stamps[148 * 4 * 16];
-#define KN_STAMP(slot)                                              \
-    do {                                                            \
-        if (tt == 0) {                                              \
-            const long long now__ = clock64();                      \
-            stamp_acc[slot] += (unsigned long long)(now__ - stamp_last); \
-            stamp_last = now__;                                     \
-        }                                                           \
-    } while (0)
-#else
-#define KN_STAMP(slot) do { } while (0)
-#endif
 
 namespace {
 
-constexpr int P_THREADS = 512, P_WARPS = 16, TEAMS = 4, TEAM = 128, HPT = H_ / TEAMS, KPAD = 128;
+constexpr int T_THREADS = 128, T_WARPS = 4, KPAD = 128;
 constexpr int XN = 48;                                   // MMA N: 16 (A-branch) + 16 (B-branch) + 2 denominators, padded to 16s
 constexpr int X_KB = (XN / 8) * 128;                     // bytes of one 8-member block of the B operand (6 core matrices)
 constexpr int X_BYTES = (KPAD / 8) * X_KB;               // 12 KB per team
 constexpr float kLeadGap = 6.f;                          // lead (log2 units) of the largest score above which its member is handled in fp32
-constexpr int SROW = 148;                                // floats per stash row: 128 numerators + 8 x (denominator, max) + pad (148 % 32 = 20: conflict-free float4 rows)
-constexpr int LREC = 144;                                // floats of a partner record: 128 numerators + 8 x (denominator, max)
+constexpr int TMEM_COLS = 128;                           // 64 columns indicator (K=128 as fp16 pairs) + 48 accumulator
+constexpr int MROW = 416;                                // floats per merge row in flight: two records (2 x 128 numerators, 2 x 16) + skip row (128)
 constexpr int ESTR = 20;                                 // floats per member in the score buffer: el (8), er (8), pad (bank spread)
-constexpr int TMEM_COLS = 512;                           // per team 128: 64 columns indicator (K=128 as fp16 pairs) + 48 accumulator
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void team_barrier(int team) { asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -119,14 +95,26 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// one row through the bulk-copy engine (global -> shared), completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+// L2 cache-policy hints: the records must survive in L2 until they are merged, everything that streams must not push them out
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void st_hint4(float4 *p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint2(float2 *p, float2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(void *smem_dst, const void *gmem_src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NPEND>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
@@ -146,35 +134,19 @@ __device__ __forceinline__ void unpack8(const uint4 q, float (&f)[8]) {
         f[2 * u] = a.x; f[2 * u + 1] = a.y;
     }
 }
-__device__ __forceinline__ void wait_flag(const int *f) {
-    unsigned long long t0 = 0;
-    while (ld_acquire_gpu(f) == 0) {
-        __nanosleep(64);
-        unsigned long long t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t0 == 0) t0 = t1;
-        else if (t1 - t0 > 4000000000ull) asm volatile("trap;");       // fail loudly instead of hanging
-    }
-}
 
-struct PLayout {
-    int R;                                                   // most rows one star finalises
-    int lrow;                                                // floats per landing row: record, + the skip row when shared memory allows
-    unsigned eler_off, x_off, elh_off, hd_off, tot_off, stash_off, land_off, rows_off, bar_off, total;
-    __host__ __device__ explicit PLayout(int n) {
-        R = n / 2;
+struct TLayout {
+    unsigned eler_off, x_off, elh_off, hd_off, tot_off, mland_off, si_off, bar_off, total;
+    __host__ __device__ explicit TLayout(int n) {
         eler_off = 0;                                        // [2][n][ESTR] fp32 scores of the current / next star
-        x_off = (2u * (unsigned)n * ESTR * 4u + 127u) & ~127u;   // [4 teams][X_BYTES] B operand
-        elh_off = x_off + TEAMS * X_BYTES;                   // [8 heads][128] fp16 centred scores el - ref
-        hd_off = elh_off + 8u * 256u;                        // [8][4] words: ref, m1, arg-max member, "arg-max handled in fp32"
-        tot_off = hd_off + 8u * 16u;                         // [4 teams][2][36] floats: TotB (16), total dB, pad, fp32 features of the leading member (16)
-        stash_off = tot_off + TEAMS * 2u * 36u * 4u;         // [3][R][SROW] floats: partials of the rows this CTA's last three stars finalise
-        land_off = stash_off + 3u * (unsigned)R * SROW * 4u; // [R][lrow] floats: partner records (+ skip rows) of the star being finalised
-        lrow = LREC + 128;
-        if (land_off + (unsigned)R * (lrow * 4u + 8u) + 64u > 227u * 1024u) lrow = LREC;   // n > 104: skip rows come through L2 instead
-        rows_off = land_off + (unsigned)R * lrow * 4u;       // [R] (node within the instance, partner vertex or ~vertex if its record is late)
-        bar_off = rows_off + (unsigned)R * 8u;               // 4 MMA mbarriers + landing mbarrier + tmem slot
-        total = bar_off + (TEAMS + 1) * 8u + 16u;
+        x_off = (2u * (unsigned)n * ESTR * 4u + 127u) & ~127u;   // [X_BYTES] B operand
+        elh_off = x_off + X_BYTES;                           // [8 heads][128] fp16 centred scores el - ref
+        hd_off = elh_off + 8u * 256u;                        // [8][4] words: ref, m1, leading member, "leading member handled in fp32"
+        tot_off = hd_off + 8u * 16u;                         // [52] floats: TotB (16), total dB, pad, fp32 features of the leading member (2 x 16, head parity)
+        mland_off = (tot_off + 56u * 4u + 15u) & ~15u;       // [4 warps][2 rows][MROW] floats: records + skip row of the merge rows in flight
+        si_off = mland_off + T_WARPS * 2u * MROW * 4u;       // slot handed out for the star after next
+        bar_off = si_off + 16u;                              // MMA mbarrier + tmem slot
+        total = bar_off + 16u;
     }
 };
 
@@ -182,70 +154,26 @@ struct PLayout {
 __device__ __forceinline__ int tri(int i, int n) { return (i * (2 * n - i - 1)) >> 1; }
 __device__ __forceinline__ int kn_local(int i, int k, int n) { return i < k ? tri(i, n) + k - i - 1 : tri(k, n) + i - k - 1; }
 
-// the rows of a star whose partner star had not published when the iteration started (rare): wait, fetch, finish.
-// Only called after this CTA's own star of the iteration is out.
-__device__ __noinline__ void finalize_late(const KnArgs &a, int n, int pb, int pi, unsigned late, const float *stash) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t pnode0 = (size_t)pb * ((size_t)n * (n - 1) / 2);
-    const float4 sc4 = __ldg(reinterpret_cast<const float4 *>(a.bn_scale) + lane), sh4 = __ldg(reinterpret_cast<const float4 *>(a.bn_shift) + lane);
-    const float4 bb4 = a.bias ? __ldg(reinterpret_cast<const float4 *>(a.bias) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < 4; ++q) {
-        if (!((late >> q) & 1u)) continue;
-        const int r = warp + P_WARPS * q;
-        int j = pi - 1 - r;
-        if (j < 0) j += n;
-        if (r >= (n - 1) / 2) j = pi + n / 2;
-        const size_t node = pnode0 + kn_local(pi, j, n);
-        wait_flag(a.flags + (size_t)pb * n + j);
-        const float4 pv = __ldcg(reinterpret_cast<const float4 *>(a.recV + node * D_) + lane);
-        const float2 pdm = __ldcg(reinterpret_cast<const float2 *>(a.recDM + node * 2 * H_) + (lane >> 2));
-        const float4 hv = __ldg(reinterpret_cast<const float4 *>(a.h + node * D_) + lane);
-        const float *Sr = stash + r * SROW;
-        const float4 v = *reinterpret_cast<const float4 *>(Sr + 4 * lane);
-        const float2 dm = *reinterpret_cast<const float2 *>(Sr + D_ + 2 * (lane >> 2));
-        const float mx = fmaxf(dm.y, pdm.y);
-        const float s1 = ex2(dm.y - mx), s2 = ex2(pdm.y - mx);
-        const float inv = 1.f / fmaf(dm.x, s1, pdm.x * s2);
-        const float a1 = s1 * inv, a2 = s2 * inv;
-        float4 o;
-        o.x = (hv.x + (fmaf(v.x, a1, pv.x * a2) + bb4.x)) * sc4.x + sh4.x;
-        o.y = (hv.y + (fmaf(v.y, a1, pv.y * a2) + bb4.y)) * sc4.y + sh4.y;
-        o.z = (hv.z + (fmaf(v.z, a1, pv.z * a2) + bb4.z)) * sc4.z + sh4.z;
-        o.w = (hv.w + (fmaf(v.w, a1, pv.w * a2) + bb4.w)) * sc4.w + sh4.w;
-        reinterpret_cast<float4 *>(a.h1 + node * D_)[lane] = o;
-        if (a.h1_tf32) reinterpret_cast<float4 *>(a.h1_tf32 + node * D_)[lane] = tf32_round4(o);
-        if ((lane & 7) == 0) discard_l2_128(a.recV + node * D_ + 4 * lane);
-    }
-}
-
-__global__ void __launch_bounds__(P_THREADS, 1) gat_kn_tc_kernel(const KnArgs a, const int total_stars) {
+__global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a, const int B) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int n = a.n;
-    const PLayout L(n);
-    const int R = L.R;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int team = warp >> 2, wq = warp & 3, tt = tid & (TEAM - 1);
+    const TLayout L(n);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, tt = tid;
     const size_t N = (size_t)n * (n - 1) / 2;
 
     float *ELER = reinterpret_cast<float *>(smem + L.eler_off);
-    unsigned char *Xs = smem + L.x_off + team * X_BYTES;
+    unsigned char *Xs = smem + L.x_off;
     __half *ELHall = reinterpret_cast<__half *>(smem + L.elh_off);
     float *HD = reinterpret_cast<float *>(smem + L.hd_off);
-    float *TOT = reinterpret_cast<float *>(smem + L.tot_off) + team * 72;   // [0,17): column totals; [20,36), [36,52): leading member's features (head parity)
-    float *STASH = reinterpret_cast<float *>(smem + L.stash_off);
-    float *LAND = reinterpret_cast<float *>(smem + L.land_off);
-    int2 *ROWS = reinterpret_cast<int2 *>(smem + L.rows_off);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bar_off);
-    uint64_t *land_bar = bars + TEAMS;
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + TEAMS + 1);
-    const int LROW = L.lrow;
-    const bool land_h = LROW > LREC;
+    float *TOT = reinterpret_cast<float *>(smem + L.tot_off);
+    float *MLAND = reinterpret_cast<float *>(smem + L.mland_off) + warp * 2 * MROW;
+    int *SI = reinterpret_cast<int *>(smem + L.si_off);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.bar_off);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bar + 1);
 
     // ---------------------------------------------------------------- setup
     if (tid == 0) {
-#pragma unroll
-        for (int t = 0; t < TEAMS; ++t) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[t])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(land_bar)), "n"(P_THREADS / 2));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -255,16 +183,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) gat_kn_tc_kernel(const KnArgs a,
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tbase = *tslot + team * 128;                        // this team's columns
-    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;               // this warp's lane quarter
+    const uint32_t tbase = *tslot;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;            // this warp's lane quarter
     const int nk = (n + 15) >> 4, nch = (n + 31) >> 5;                 // MMAs (16 members each) / indicator chunks (32 members each)
-    unsigned char *xrow = Xs + (tt >> 3) * X_KB + (tt & 7) * 16;       // this member's row of the B operand (6 pieces, 128 B apart)
-    const int G = gridDim.x, step_b = G / n, step_i = G - step_b * n;  // the next star of this CTA is G stars further
-    const int half_rows = (n - 1) >> 1;
+    unsigned char *xrow = Xs + (tt >> 3) * X_KB + (tt & 7) * 16;       // this member's row of the B operand (pieces 128 B apart)
+    const int total = B * n;                                           // star slots = merge slices
 
     // scores of star (sb, si) -> buffer `buf` (cp.async; the vertex's own slot is zero-filled)
-    auto issue_scores = [&](int sb, int si, int buf, int t0, int nthreads) {
-        for (int idx = t0; idx < 4 * n; idx += nthreads) {
+    auto issue_scores = [&](int sb, int si, int buf) {
+        for (int idx = tid; idx < 4 * n; idx += T_THREADS) {
             const int k = idx >> 2, p = idx & 3;
             float *dst = ELER + (buf * n + k) * ESTR + p * 4;
             if (k != si) cp_async16(dst, (p < 2 ? a.el : a.er) + ((size_t)sb * N + kn_local(si, k, n)) * H_ + (p & 1) * 4);
@@ -272,54 +199,79 @@ __global__ void __launch_bounds__(P_THREADS, 1) gat_kn_tc_kernel(const KnArgs a,
         }
     };
 
-    // (b, i) of this CTA's star of the iteration, of the next one, and of the last two (b < 0: none)
-    int cur = blockIdx.x, cb = cur / n, ci = cur - cb * n;
-    int b1 = -1, i1 = 0, b2 = -1, i2 = 0;
-    if (cur < total_stars) issue_scores(cb, ci, 0, tid, P_THREADS);
+    const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+    int *ctr = a.flags + B, *mctr = ctr + 1;                           // star-slot / merge-slice counters (zeroed with the per-instance counters)
+    if (tid == 0) {
+        SI[0] = atomicAdd(ctr, 1);
+        SI[1] = atomicAdd(ctr, 1);
+    }
+    __syncthreads();
+    int cur = SI[0], nxt = SI[1];                                      // star slots are handed out in order, one star ahead
+    int mcur = -1, mpend = -1;                                         // merge slice of this iteration / taken but its instance not complete yet
+    __syncthreads();
+    if (cur < total) issue_scores(cur / n, cur % n, 0);
     cp_async_commit();
-#ifdef KN_STAMPS
-    unsigned long long stamp_acc[16] = {};
-    long long stamp_last = clock64();
-#endif
-    uint32_t parity = 0, land_parity = 0;
-    unsigned late = 0u;                                                // rows of the previous iteration's prev still to finish (this warp)
-    int late_b = 0, late_i = 0, late_buf = 0;
+    uint32_t parity = 0;
 
-    for (int it = 0;; ++it) {
-        const bool havecur = cur < total_stars, haveprev = b2 >= 0;    // prev = (b2, i2): the star finalised in this iteration
-        if (!havecur && b1 < 0 && b2 < 0) break;
-        const int cbuf = it & 1, sbuf = it % 3, pbuf = (it + 1) % 3;  // score buffer / stash of the current star / stash of prev
-        const int b = cb, i = ci;
-        int nb = cb + step_b, ni = ci + step_i;                        // next star
-        if (ni >= n) { ni -= n; ++nb; }
-        // ---- top of the iteration, part A: requests whose answers are needed later on
-        // this thread as member / destination row tt of the current star; its features for the team's first head
-        const bool live = havecur && tt < n && tt != i;
+    for (int it = 0; cur < total || mcur >= 0 || mpend >= 0; ++it) {
+        const int b = cur / n, i = cur - b * n, cbuf = it & 1;
+        const bool havestar = cur < total;
+        // Merge slices (instance bm, nodes [mlo, mhi)) are handed out in order too, but a CTA only merges a slice once all n stars of
+        // its instance are out; until then it keeps the slice and carries on with its stars.  Nothing a star does waits for a merge.
+        const bool havemerge = mcur >= 0;
+        const int bm = havemerge ? mcur / n : 0, im = mcur - bm * n;
+        const int mlo = (im * (n - 1)) >> 1, mhi = havemerge ? ((im + 1) * (n - 1)) >> 1 : 0;
+        const size_t mnode0 = (size_t)bm * N;
+        int grabbed = 0, mtake = -1;
+        if (tid == 0) {
+            grabbed = atomicAdd(ctr, 1);                               // the slot after next (needed at the end of the iteration)
+            if (mpend < 0) mtake = atomicAdd(mctr, 1);                 // the slice to merge in the next iteration
+        }
+        // this thread as member / destination row tt of the current star; its features for the first head
+        const bool live = havestar && tt < n && tt != i;
         const int my_local = live ? kn_local(i, tt, n) : 0;
-        const uint4 *ftrow = reinterpret_cast<const uint4 *>(static_cast<const unsigned char *>(a.ft) + ((size_t)b * N + my_local) * 256);
+        const size_t my_node = (size_t)b * N + my_local;
+        const uint4 *ftrow = reinterpret_cast<const uint4 *>(static_cast<const unsigned char *>(a.ft) + my_node * 256);
         uint4 f0 = make_uint4(0u, 0u, 0u, 0u), f1 = f0;
-        if (live) { f0 = __ldg(ftrow + 2 * team * HPT); f1 = __ldg(ftrow + 2 * team * HPT + 1); }
-        const int Rp = haveprev ? half_rows + (((n & 1) == 0 && i2 < (n >> 1)) ? 1 : 0) : 0;
-        KN_STAMP(0);                                                   // top A
-        cp_async_wait_group<0>();                                      // the current star's scores (requested an iteration ago)
-        __syncthreads();                                               // ... and every warp has finished the previous iteration
-        KN_STAMP(1);                                                   // wait scores + barrier 1
-#ifdef KN_STAMPS
-        if (tt == 0) stamp_acc[12] += __popc(late);
-#endif
-        if (late) finalize_late(a, n, late_b, late_i, late, STASH + late_buf * R * SROW);   // (per warp; rare)
-        KN_STAMP(2);                                                   // late rows
+        if (live) { f0 = __ldg(ftrow); f1 = __ldg(ftrow + 1); }
+        if (havemerge) {
+            // skip rows of the merge slice: bring them into L2 now, they are fetched one MMA shadow before they are used
+            for (int idx = tid; idx < (mhi - mlo) * 4; idx += T_THREADS)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h + (mnode0 + mlo) * D_ + 32 * idx));
+        }
+        cp_async_wait_group<0>();                                      // the current star's scores (requested a star ago)
+        __syncthreads();
+        if (nxt < total) issue_scores(nxt / n, nxt % n, cbuf ^ 1);
+        // merge rows of MMA shadow `hs` (this warp: rows mlo + 4 hs + warp, + 32): records of both stars and skip row -> shared memory
+        auto fetch_merge_rows = [&](int hs) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int r = mlo + hs * T_WARPS + warp + 32 * q;
+                if (r >= mhi) break;
+                const size_t node = mnode0 + r;
+                float *dst = MLAND + q * MROW;
+                const float *rv = a.recV + node * 2 * D_;
+                cp_async16_hint(dst + 4 * lane, rv + 4 * lane, pol_stream);
+                cp_async16_hint(dst + D_ + 4 * lane, rv + D_ + 4 * lane, pol_stream);
+                if (lane < 8) cp_async16_hint(dst + 2 * D_ + 4 * lane, a.recDM + node * 4 * H_ + 4 * lane, pol_stream);
+                cp_async16_hint(dst + 2 * D_ + 32 + 4 * lane, a.h + node * D_ + 4 * lane, pol_stream);
+            }
+        };
+        if (havemerge) fetch_merge_rows(0);
+        cp_async_commit();
         const float *E = ELER + cbuf * n * ESTR;
-        if (warp < H_) {
-            // ---- warps 0..7: top-2 of el per head (warp w = head w); the fp16 copy of the CENTRED scores that the branch decision uses
-            if (havecur) {
+        if (havestar) {
+            // ---- top-2 of el per head (each warp two heads); the fp16 copy of the CENTRED scores that the branch decision uses
+#pragma unroll
+            for (int hq = 0; hq < H_ / T_WARPS; ++hq) {
+                const int head = warp * (H_ / T_WARPS) + hq;
                 float ev[KPAD / 32];
                 Top2 t2{-INFINITY, -INFINITY, 0};
 #pragma unroll
                 for (int q = 0; q < KPAD / 32; ++q) {
                     const int k = lane + 32 * q;
                     const bool ok = k < n && k != i;
-                    ev[q] = ok ? E[k * ESTR + warp] : -INFINITY;
+                    ev[q] = ok ? E[k * ESTR + head] : -INFINITY;
                     if (ok) t2 = top2_merge(t2, Top2{ev[q], -INFINITY, k});
                 }
 #pragma unroll
@@ -333,111 +285,58 @@ __global__ void __launch_bounds__(P_THREADS, 1) gat_kn_tc_kernel(const KnArgs a,
                 const bool fix = t2.m1 - t2.m2 > kLeadGap;             // (n >= 3: the runner-up exists)
                 const float ref = fix ? t2.m2 : t2.m1;
 #pragma unroll
-                for (int q = 0; q < KPAD / 32; ++q) ELHall[warp * KPAD + lane + 32 * q] = __float2half_rn(ev[q] - ref);
-                if (lane == 0) *reinterpret_cast<float4 *>(HD + warp * 4) = make_float4(ref, t2.m1, __int_as_float(t2.a1), __int_as_float(fix ? 1 : 0));
+                for (int q = 0; q < KPAD / 32; ++q) ELHall[head * KPAD + lane + 32 * q] = __float2half_rn(ev[q] - ref);
+                if (lane == 0) *reinterpret_cast<float4 *>(HD + head * 4) = make_float4(ref, t2.m1, __int_as_float(t2.a1), __int_as_float(fix ? 1 : 0));
             }
-        } else {
-            // ---- warps 8..15: everything this and the next iteration will read from global memory is requested here
-            const int lw = warp - H_;                                  // rows lw + 8 q, q = 0..7
-            if (lw == 0 && lane == 0 && b1 >= 0) {                     // the previous star's records are all written (barrier above): publish
-                __threadfence();
-                st_release_gpu(a.flags + b1 * n + i1, 1);
-            }
-            bool arrived = false;
-            if (haveprev) {
-                const size_t pnode0 = (size_t)b2 * N;
-                const int r = lw + 8 * lane;                           // lanes 0..7: one row each, fetched by the bulk-copy engine
-                if (lane < 8 && r < Rp) {
-                    int j = i2 - 1 - r;
-                    if (j < 0) j += n;
-                    if (r >= half_rows) j = i2 + (n >> 1);
-                    const int nl = kn_local(i2, j, n);
-                    const uint32_t dst = smem_u32(LAND + r * LROW), bar = smem_u32(land_bar);
-                    const float *hrow = a.h + (pnode0 + nl) * D_;
-                    if (land_h) bulk_g2s(dst + LREC * 4, hrow, 512, bar);  // skip row: no dependency
-                    else asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;" ::"l"(hrow) : "memory");
-                    // Partner stars published a whole iteration ago, normally.  This is a look, not a wait: this CTA's current star is
-                    // not out yet, and a partner's CTA may in turn need it.  Late rows are finished after the next iteration's barrier.
-                    const int fl = ld_acquire_gpu(a.flags + (size_t)b2 * n + j);
-                    ROWS[r] = make_int2(nl, fl != 0 ? j : ~j);
-                    mbar_arrive_expect_tx(bar, (land_h ? 512u : 0u) + (fl != 0 ? (uint32_t)LREC * 4u : 0u));
-                    if (fl != 0) {
-                        asm volatile("fence.proxy.async.global;" ::: "memory");    // the copies below read what the flag guards
-                        bulk_g2s(dst, a.recV + (pnode0 + nl) * D_, 512, bar);
-                        bulk_g2s(dst + 512, a.recDM + (pnode0 + nl) * 2 * H_, 64, bar);
-                    }
-                    arrived = true;
-                }
-            }
-            // the landing mbarrier completes its phase when all 256 loader threads have arrived and every byte announced has landed
-            if (!arrived) mbar_arrive(smem_u32(land_bar));
-            if (cur + G < total_stars) issue_scores(nb, ni, cbuf ^ 1, tid - P_THREADS / 2, P_THREADS / 2);
-            cp_async_commit();
+            __syncthreads();
         }
-        KN_STAMP(3);                                                   // top-2 | requests
-        __syncthreads();                                               // heads' references and centred scores, row table visible
-        KN_STAMP(4);                                                   // barrier 2
 
-        // two rows of prev (q0, q0 + 1 of this warp's four): merge the landed partner record with the stashed partial and finish.
-        // This star's partial first, the partner's second -- who finalises is a function of (i, j, n) only, so the result is
-        // deterministic.  Runs in the shadow of an MMA.
-        auto finalize_prev = [&](int q0) {
-            if (warp + P_WARPS * q0 >= Rp) return;
-            const size_t pnode0 = (size_t)b2 * N;
-            const float *hb = a.h + pnode0 * D_;
-            float *h1b = a.h1 + pnode0 * D_;
-            const float *stash = STASH + pbuf * R * SROW;
+        // the merge rows fetched one shadow ago: combine the two stars' records in fixed (lower, higher) order, apply bias + skip +
+        // BN1, write h1; then fetch the rows of the next shadow
+        auto merge_rows = [&](int hs) {
             const float4 sc4 = __ldg(reinterpret_cast<const float4 *>(a.bn_scale) + lane), sh4 = __ldg(reinterpret_cast<const float4 *>(a.bn_shift) + lane);
             const float4 bb4 = a.bias ? __ldg(reinterpret_cast<const float4 *>(a.bias) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-            int2 row[2];
-            float4 hv[2];
+            cp_async_wait_group<0>();
+            __syncwarp();
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const int r = warp + P_WARPS * (q0 + q);
-                row[q] = (r < Rp) ? ROWS[r] : make_int2(0, -1);
-                if (!land_h) hv[q] = __ldg(reinterpret_cast<const float4 *>(hb + row[q].x * D_) + lane);   // (prefetched into L2)
-            }
-            mbar_wait(land_bar, land_parity);                          // the loader warps' copies have landed
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int r = warp + P_WARPS * (q0 + q);
-                if (r >= Rp || row[q].y < 0) continue;                 // (late partner: finished after the next iteration's barrier)
-                const float *Lr = LAND + r * LROW, *Sr = stash + r * SROW;
-                if (land_h) hv[q] = *reinterpret_cast<const float4 *>(Lr + LREC + 4 * lane);
-                const float4 pv = *reinterpret_cast<const float4 *>(Lr + 4 * lane), v = *reinterpret_cast<const float4 *>(Sr + 4 * lane);
-                const float2 pdm = *reinterpret_cast<const float2 *>(Lr + D_ + 2 * (lane >> 2)), dm = *reinterpret_cast<const float2 *>(Sr + D_ + 2 * (lane >> 2));
-                const float mx = fmaxf(dm.y, pdm.y);
-                const float s1 = ex2(dm.y - mx), s2 = ex2(pdm.y - mx);
-                const float inv = rcp_approx(fmaf(dm.x, s1, pdm.x * s2));
+                const int r = mlo + hs * T_WARPS + warp + 32 * q;
+                if (r >= mhi) break;
+                const size_t node = mnode0 + r;
+                const float *Lr = MLAND + q * MROW;
+                const float4 lv = *reinterpret_cast<const float4 *>(Lr + 4 * lane), uv = *reinterpret_cast<const float4 *>(Lr + D_ + 4 * lane);
+                const float2 l2 = *reinterpret_cast<const float2 *>(Lr + 2 * D_ + 2 * (lane >> 2)), u2 = *reinterpret_cast<const float2 *>(Lr + 2 * D_ + 16 + 2 * (lane >> 2));
+                const float4 hv = *reinterpret_cast<const float4 *>(Lr + 2 * D_ + 32 + 4 * lane);
+                const float mx = fmaxf(l2.y, u2.y);
+                const float s1 = ex2(l2.y - mx), s2 = ex2(u2.y - mx);
+                const float inv = rcp_approx(fmaf(l2.x, s1, u2.x * s2));
                 const float a1 = s1 * inv, a2 = s2 * inv;
                 float4 o;
-                o.x = (hv[q].x + (fmaf(v.x, a1, pv.x * a2) + bb4.x)) * sc4.x + sh4.x;
-                o.y = (hv[q].y + (fmaf(v.y, a1, pv.y * a2) + bb4.y)) * sc4.y + sh4.y;
-                o.z = (hv[q].z + (fmaf(v.z, a1, pv.z * a2) + bb4.z)) * sc4.z + sh4.z;
-                o.w = (hv[q].w + (fmaf(v.w, a1, pv.w * a2) + bb4.w)) * sc4.w + sh4.w;
-                reinterpret_cast<float4 *>(h1b + row[q].x * D_)[lane] = o;
-                if (a.h1_tf32) reinterpret_cast<float4 *>(a.h1_tf32 + (pnode0 + row[q].x) * D_)[lane] = tf32_round4(o);
-                // the consumed numerator record is dead (read exactly once): drop its dirty L2 lines instead of writing them back
-                if ((lane & 7) == 0) discard_l2_128(a.recV + (pnode0 + row[q].x) * D_ + 4 * lane);
+                o.x = (hv.x + (fmaf(lv.x, a1, uv.x * a2) + bb4.x)) * sc4.x + sh4.x;
+                o.y = (hv.y + (fmaf(lv.y, a1, uv.y * a2) + bb4.y)) * sc4.y + sh4.y;
+                o.z = (hv.z + (fmaf(lv.z, a1, uv.z * a2) + bb4.z)) * sc4.z + sh4.z;
+                o.w = (hv.w + (fmaf(lv.w, a1, uv.w * a2) + bb4.w)) * sc4.w + sh4.w;
+                st_hint4(reinterpret_cast<float4 *>(a.h1 + node * D_) + lane, o, pol_stream);
+                if (a.h1_tf32) st_hint4(reinterpret_cast<float4 *>(a.h1_tf32 + node * D_) + lane, tf32_round4(o), pol_stream);
+                // the consumed records are dead (read exactly once): drop their dirty L2 lines instead of writing them back
+                if (lane < 8) discard_l2_128(a.recV + node * 2 * D_ + 32 * lane);
+                else if (lane == 8) discard_l2_128(a.recDM + node * 4 * H_);
             }
+            __syncwarp();
+            if (hs + 1 < H_) fetch_merge_rows(hs + 1);
+            cp_async_commit();
         };
 
-        if (havecur) {
-            // which of the two stars of destination {i, tt} finalises it
-            int dist = i - tt;
-            if (dist < 0) dist += n;
-            const bool fin = live && (2 * dist < n || (2 * dist == n && i < tt));
-            float *srow = STASH + (sbuf * R + ((2 * dist == n) ? half_rows : dist - 1)) * SROW;
-#pragma unroll
-            for (int hh = 0; hh < HPT; ++hh) {
-                const int head = team * HPT + hh;
+#pragma unroll 1
+        for (int head = 0; head < H_; ++head) {
+            if (havestar) {
                 const float4 hd = *reinterpret_cast<const float4 *>(HD + head * 4);   // ref, m1, leading member, "leading member in fp32"
                 const float ref = hd.x;
-                const bool fix = __float_as_int(hd.w) != 0;            // team-uniform
+                const bool fix = __float_as_int(hd.w) != 0;            // CTA-uniform
                 const bool lead = fix && tt == __float_as_int(hd.z);
                 const float erh = live ? E[tt * ESTR + 8 + head] : 0.f;
                 const __half th16 = live ? __float2half_rn(-erh - ref) : __float2half_rn(tt == i ? -INFINITY : INFINITY);
-                float *TOTl = TOT + 20 + (hh & 1) * 16;                // fp32 features of the leading member (parity buffer)
+                float *TOTl = TOT + 20 + (head & 1) * 16;              // fp32 features of the leading member (parity buffer)
                 // ---- B operand row of member tt: [A ft | A' ft | A A' 0...]
                 if (tt < 16 * nk) {
                     uint4 xa0 = make_uint4(0u, 0u, 0u, 0u), xa1 = xa0, xb0 = xa0, xb1 = xa0, xd = xa0;
@@ -469,9 +368,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) gat_kn_tc_kernel(const KnArgs a,
                     *reinterpret_cast<uint4 *>(xrow + 128) = xa1;
                     *reinterpret_cast<uint4 *>(xrow + 256) = xb0;
                     *reinterpret_cast<uint4 *>(xrow + 384) = xb1;
-                    *reinterpret_cast<uint4 *>(xrow + 512) = xd;
+                    *reinterpret_cast<uint4 *>(xrow + 512) = xd;       // (columns 40..47 of the operand are never read back: left as they are)
                 }
-                if (live && hh + 1 < HPT) { f0 = __ldg(ftrow + 2 * (head + 1)); f1 = __ldg(ftrow + 2 * (head + 1) + 1); }   // next head's features
+                if (live && head + 1 < H_) { f0 = __ldg(ftrow + 2 * (head + 1)); f1 = __ldg(ftrow + 2 * (head + 1) + 1); }   // next head's features
                 // ---- indicator row of destination tt: I[tt][k] = [el_k - ref >= -er_tt - ref] as fp16 1.0 / 0.0, straight into tensor
                 // memory.  Row i (the vertex itself, not a destination) takes threshold -inf: its accumulator row is the column totals.
                 {
@@ -492,26 +391,24 @@ __global__ void __launch_bounds__(P_THREADS, 1) gat_kn_tc_kernel(const KnArgs a,
                         tmem_st16(tbase + lane_sel + c * 16, v);
                     }
                 }
-                KN_STAMP(5);                                           // operand row + indicator
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // B operand written through the generic proxy
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                team_barrier(team);                                    // operands complete
+                __syncthreads();                                       // operands complete
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (tt == 0) {
+                if (tid == 0) {
                     for (int ks = 0; ks < nk; ++ks)
                         umma_f16_ts(tbase + 64, tbase + ks * 8, make_mn_desc(smem_u32(Xs) + ks * 2 * X_KB, X_KB, 128), kIdesc, ks != 0);
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[team])) : "memory");
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
                 }
                 __syncwarp();
-                KN_STAMP(6);                                           // barrier A + MMA issue
-                if (haveprev) finalize_prev(2 * hh);                   // in the shadow of the MMA
-                KN_STAMP(7);                                           // two rows of prev
+            }
+            if (havemerge) merge_rows(head);                           // in the shadow of the MMA chain
+            if (havestar) {
                 // ---- accumulators
                 uint32_t SA[16], SB[16], SD0, SD1;
-                mbar_wait(&bars[team], parity);
+                mbar_wait(bar, parity);
                 parity ^= 1;
-                KN_STAMP(8);                                           // rest of the MMA
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 tmem_ld16(tbase + lane_sel + 64, SA);
                 tmem_ld16(tbase + lane_sel + 80, SB);
@@ -524,11 +421,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) gat_kn_tc_kernel(const KnArgs a,
                         *reinterpret_cast<uint4 *>(TOT + 4 * q) = make_uint4(SB[4 * q], SB[4 * q + 1], SB[4 * q + 2], SB[4 * q + 3]);
                     TOT[16] = __uint_as_float(SD1);
                 }
-                KN_STAMP(9);                                           // accumulators -> registers
-                team_barrier(team);                                    // totals visible; every row has its accumulators
-                KN_STAMP(10);                                          // barrier B
+                __syncthreads();                                       // totals visible; every row has its accumulators
                 if (live) {
                     // ---- this star's partial for destination tt (fp32): v = C1 SA + C2 (Tot - SB) - self (+ leading member)
+                    const float4 hd = *reinterpret_cast<const float4 *>(HD + head * 4);
+                    const float ref = hd.x;
+                    const bool fix = __float_as_int(hd.w) != 0;
+                    const bool lead = fix && tt == __float_as_int(hd.z);
+                    const float erh = E[tt * ESTR + 8 + head];
+                    const __half th16 = __float2half_rn(-erh - ref);
                     const float s = ref + erh;
                     const float c = ex2(-0.8f * fabsf(s));
                     const float C1 = s >= 0.f ? 1.f : c, C2 = s >= 0.f ? c : 1.f;
@@ -547,7 +448,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) gat_kn_tc_kernel(const KnArgs a,
                     }
                     const float k1 = C1 * scl, k2 = C2 * scl, ks = (self_a ? C1 : C2) * scl;
                     const unsigned char *xself = xrow + (self_a ? 0 : 256);        // this member's own products in the branch it was counted in
-                    float *rv = a.recV + ((size_t)b * N + my_local) * D_ + head * F_;
+                    const int sl = i < tt ? 0 : 1;                     // slot 0: written by the star of the lower vertex
+                    float4 *rv = reinterpret_cast<float4 *>(a.recV + (my_node * 2 + sl) * D_ + head * F_);
+                    const float *TOTl = TOT + 20 + (head & 1) * 16;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {                      // 4 features at a time
                         const float4 t4 = *reinterpret_cast<const float4 *>(TOT + 4 * q);
@@ -558,41 +461,40 @@ __global__ void __launch_bounds__(P_THREADS, 1) gat_kn_tc_kernel(const KnArgs a,
                         v.y = fmaf(k1, __uint_as_float(SA[4 * q + 1]), fmaf(-k2, __uint_as_float(SB[4 * q + 1]), fmaf(-ks, x01.y, k2 * t4.y)));
                         v.z = fmaf(k1, __uint_as_float(SA[4 * q + 2]), fmaf(-k2, __uint_as_float(SB[4 * q + 2]), fmaf(-ks, x23.x, k2 * t4.z)));
                         v.w = fmaf(k1, __uint_as_float(SA[4 * q + 3]), fmaf(-k2, __uint_as_float(SB[4 * q + 3]), fmaf(-ks, x23.y, k2 * t4.w)));
-                        if (addlead) {
-                            const float4 l4 = *reinterpret_cast<const float4 *>(TOTl + 4 * q);
-                            v.x += l4.x; v.y += l4.y; v.z += l4.z; v.w += l4.w;
+                        if (__any_sync(__activemask(), addlead)) {     // (rare: a real branch, not predicated instructions)
+                            if (addlead) {
+                                const float4 l4 = *reinterpret_cast<const float4 *>(TOTl + 4 * q);
+                                v.x += l4.x; v.y += l4.y; v.z += l4.z; v.w += l4.w;
+                            }
                         }
-                        if (fin) *reinterpret_cast<float4 *>(srow + head * F_ + 4 * q) = v;
-                        else __stcg(reinterpret_cast<float4 *>(rv) + q, v);
+                        st_hint4(rv + q, v, pol_keep);
                     }
-                    if (fin) *reinterpret_cast<float2 *>(srow + D_ + 2 * head) = make_float2(den, M);
-                    else __stcg(reinterpret_cast<float2 *>(a.recDM + ((size_t)b * N + my_local) * 2 * H_ + 2 * head), make_float2(den, M));
+                    st_hint2(reinterpret_cast<float2 *>(a.recDM + (my_node * 2 + sl) * 2 * H_ + 2 * head), make_float2(den, M), pol_keep);
                 }
-                KN_STAMP(11);                                          // partial
             }
-        } else if (haveprev) {
-            finalize_prev(0);
-            finalize_prev(2);
         }
-        // rows whose partner was late wait until this CTA's own star of the iteration is out (after the next iteration's first barrier)
-        late = 0u;
-        if (haveprev) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (warp + P_WARPS * q < Rp && ROWS[warp + P_WARPS * q].y < 0) late |= 1u << q;
-            late_b = b2; late_i = i2; late_buf = pbuf;
+        if (tid == 0) {
+            int cand = mpend >= 0 ? mpend : mtake;
+            if (cand >= total) cand = -1;                              // no slices left
+            int rdy = 0;
+            if (cand >= 0) {
+                rdy = ld_acquire_gpu(a.flags + cand / n) >= n;         // a look, not a wait
+                if (!rdy && !havestar) __nanosleep(1000);              // (only merging left: do not hammer the counter)
+            }
+            SI[0] = grabbed; SI[1] = cand; SI[2] = rdy;
         }
-        land_parity ^= 1;                                              // (the loader warps arrive once per iteration)
-        b2 = b1; i2 = i1;
-        b1 = havecur ? b : -1; i1 = i;
-        cur += G; cb = nb; ci = ni;
+        __syncthreads();                                               // this star's records are all written; next slot / slice known
+        if (havestar && tid == 0) {
+            __threadfence();
+            atomicAdd(a.flags + b, 1);                                 // one more star of instance b is out
+        }
+        cur = nxt;
+        nxt = SI[0];
+        mcur = SI[2] ? SI[1] : -1;
+        mpend = SI[2] ? -1 : SI[1];
+        __syncthreads();                                               // (SI is rewritten in the next iteration)
     }
-#ifdef KN_STAMPS
-    if (tt == 0 && blockIdx.x < 148)
-        for (int k = 0; k < 16; ++k) g_kn_stamps[(blockIdx.x * 4 + team) * 16 + k] = stamp_acc[k];
-#endif
     // ---------------------------------------------------------------- teardown
-    if (late) finalize_late(a, n, late_b, late_i, late, STASH + late_buf * R * SROW);       // (all stars of this CTA are out)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tslot), "n"(TMEM_COLS) : "memory");
@@ -601,28 +503,29 @@ __global__ void __launch_bounds__(P_THREADS, 1) gat_kn_tc_kernel(const KnArgs a,
 }  // namespace
 
 namespace gnngls {
-int launch_kn_tc(const KnArgs &args, int B, cudaStream_t st) {
-    const PLayout L(args.n);
-    GNNGLS_REQUIRE(args.n <= KPAD, GNNGLS_ERR_UNSUPPORTED, "the tcgen05 K_n kernel handles n <= %d", KPAD);
+size_t kn_tc_workspace_bytes(int B, int n) {
+    const size_t M = (size_t)B * ((size_t)n * (n - 1) / 2);
+    return sizeof(float) * M * (2 * D_ + 4 * H_) + sizeof(int) * ((size_t)B + 4);   // two records per node, one counter per instance, slot + slice counters
+}
+
+int launch_kn_tc(const KnArgs &args_in, int B, void *workspace, cudaStream_t st) {
+    KnArgs args = args_in;
+    const int n = args.n;
+    const TLayout L(n);
+    GNNGLS_REQUIRE(n <= KPAD, GNNGLS_ERR_UNSUPPORTED, "the tcgen05 K_n kernel handles n <= %d", KPAD);
+    const size_t M = (size_t)B * ((size_t)n * (n - 1) / 2);
+    args.recV = static_cast<float *>(workspace);
+    args.recDM = args.recV + M * 2 * D_;
+    args.flags = reinterpret_cast<int *>(args.recDM + M * 4 * H_);
+    GNNGLS_CUDA_OK(cudaMemsetAsync(args.flags, 0, sizeof(int) * ((size_t)B + 4), st));
     GNNGLS_CUDA_OK(cudaFuncSetAttribute(gat_kn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    const int64_t stars = (int64_t)B * args.n;
+    GNNGLS_CUDA_OK(cudaFuncSetAttribute(gat_kn_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    const int64_t stars = (int64_t)B * n;
     GNNGLS_REQUIRE(stars < ((int64_t)1 << 30), GNNGLS_ERR_UNSUPPORTED, "B*n too large for one launch");
-    const int sms = gnngls::device_sm_count();
-    const unsigned grid = (unsigned)(stars < sms ? stars : sms);
-    gat_kn_tc_kernel<<<grid, P_THREADS, L.total, st>>>(args, (int)stars);
+    const int grid_max = gnngls::device_sm_count() * 4;
+    const unsigned grid = (unsigned)(stars < grid_max ? stars : grid_max);
+    gat_kn_tc_kernel<<<grid, T_THREADS, L.total, st>>>(args, B);
     GNNGLS_LAUNCH_OK("gat_kn_tc_kernel");
     return GNNGLS_OK;
 }
 }  // namespace gnngls
-
-// debug: per-(CTA, team) phase cycle totals of the last launch (zeros unless built with -DKN_STAMPS)
-extern "C" int gnngls_debug_kn_stamps(unsigned long long *out, int count) {
-#ifdef KN_STAMPS
-    if (count > 148 * 4 * 16) count = 148 * 4 * 16;
-    GNNGLS_CUDA_OK(cudaMemcpyFromSymbol(out, g_kn_stamps, sizeof(unsigned long long) * count));
-    return GNNGLS_OK;
-#else
-    (void)out; (void)count;
-    return GNNGLS_ERR_UNSUPPORTED;
-#endif
-}

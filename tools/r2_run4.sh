@@ -3,7 +3,7 @@
 set -u
 O=gpurun_out; T=${1:-r2g}
 mkdir -p $O
-for c in "3 3" "4 5" "20 40" "50 9" "100 3" "101 4" "127 3" "128 3" "128 40 0" "100 256 0 20" "127 3" "128 5"; do timeout 120 python tools/kn_case.py $c 2>&1 | tail -1; done
+for c in "3 3" "4 5" "20 40" "50 9" "100 3" "101 4" "127 3" "128 3" "128 40 0" "100 256 0 20" "127 3" "128 5" "100 30 0"; do timeout 120 python tools/kn_case.py $c 2>&1 | tail -1; done
 timeout 120 python tools/kn_bench.py 100 256 20
 timeout 120 python tools/kn_bench.py 50 1024 20
 timeout 120 python tools/kn_bench.py 20 4096 20
