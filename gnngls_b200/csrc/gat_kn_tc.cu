@@ -356,7 +356,15 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                         xa0 = mul4(f0, hA); xa1 = mul4(f1, hA); xb0 = mul4(f0, hB); xb1 = mul4(f1, hB);
                         const __half2 dd = __halves2half2(A16, A516);
                         xd.x = *reinterpret_cast<const uint32_t *>(&dd);
-                    } else if (live) {                                 // the leading member of this head: fp32 features for the epilogue
+                    }
+                    *reinterpret_cast<uint4 *>(xrow) = xa0;
+                    *reinterpret_cast<uint4 *>(xrow + 128) = xa1;
+                    *reinterpret_cast<uint4 *>(xrow + 256) = xb0;
+                    *reinterpret_cast<uint4 *>(xrow + 384) = xb1;
+                    *reinterpret_cast<uint4 *>(xrow + 512) = xd;       // (columns 40..47 of the operand are never read back: left as they are)
+                }
+                if (fix) {                                             // (rare) the leading member of this head: fp32 features for the epilogue
+                    if (lead) {
                         float ff[16];
                         unpack8(f0, reinterpret_cast<float(&)[8]>(ff[0]));
                         unpack8(f1, reinterpret_cast<float(&)[8]>(ff[8]));
@@ -364,11 +372,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                         for (int q = 0; q < 4; ++q)
                             *reinterpret_cast<float4 *>(TOTl + 4 * q) = make_float4(ff[4 * q], ff[4 * q + 1], ff[4 * q + 2], ff[4 * q + 3]);
                     }
-                    *reinterpret_cast<uint4 *>(xrow) = xa0;
-                    *reinterpret_cast<uint4 *>(xrow + 128) = xa1;
-                    *reinterpret_cast<uint4 *>(xrow + 256) = xb0;
-                    *reinterpret_cast<uint4 *>(xrow + 384) = xb1;
-                    *reinterpret_cast<uint4 *>(xrow + 512) = xd;       // (columns 40..47 of the operand are never read back: left as they are)
+                    __syncwarp();
                 }
                 if (live && head + 1 < H_) { f0 = __ldg(ftrow + 2 * (head + 1)); f1 = __ldg(ftrow + 2 * (head + 1) + 1); }   // next head's features
                 // ---- indicator row of destination tt: I[tt][k] = [el_k - ref >= -er_tt - ref] as fp16 1.0 / 0.0, straight into tensor
@@ -451,24 +455,29 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                     const int sl = i < tt ? 0 : 1;                     // slot 0: written by the star of the lower vertex
                     float4 *rv = reinterpret_cast<float4 *>(a.recV + (my_node * 2 + sl) * D_ + head * F_);
                     const float *TOTl = TOT + 20 + (head & 1) * 16;
+                    float4 v[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {                      // 4 features at a time
                         const float4 t4 = *reinterpret_cast<const float4 *>(TOT + 4 * q);
                         const uint2 xs = *reinterpret_cast<const uint2 *>(xself + (q >> 1) * 128 + (q & 1) * 8);
                         const float2 x01 = __half22float2(*reinterpret_cast<const __half2 *>(&xs.x)), x23 = __half22float2(*reinterpret_cast<const __half2 *>(&xs.y));
-                        float4 v;
-                        v.x = fmaf(k1, __uint_as_float(SA[4 * q]), fmaf(-k2, __uint_as_float(SB[4 * q]), fmaf(-ks, x01.x, k2 * t4.x)));
-                        v.y = fmaf(k1, __uint_as_float(SA[4 * q + 1]), fmaf(-k2, __uint_as_float(SB[4 * q + 1]), fmaf(-ks, x01.y, k2 * t4.y)));
-                        v.z = fmaf(k1, __uint_as_float(SA[4 * q + 2]), fmaf(-k2, __uint_as_float(SB[4 * q + 2]), fmaf(-ks, x23.x, k2 * t4.z)));
-                        v.w = fmaf(k1, __uint_as_float(SA[4 * q + 3]), fmaf(-k2, __uint_as_float(SB[4 * q + 3]), fmaf(-ks, x23.y, k2 * t4.w)));
-                        if (__any_sync(__activemask(), addlead)) {     // (rare: a real branch, not predicated instructions)
-                            if (addlead) {
+                        v[q].x = fmaf(k1, __uint_as_float(SA[4 * q]), fmaf(-k2, __uint_as_float(SB[4 * q]), fmaf(-ks, x01.x, k2 * t4.x)));
+                        v[q].y = fmaf(k1, __uint_as_float(SA[4 * q + 1]), fmaf(-k2, __uint_as_float(SB[4 * q + 1]), fmaf(-ks, x01.y, k2 * t4.y)));
+                        v[q].z = fmaf(k1, __uint_as_float(SA[4 * q + 2]), fmaf(-k2, __uint_as_float(SB[4 * q + 2]), fmaf(-ks, x23.x, k2 * t4.z)));
+                        v[q].w = fmaf(k1, __uint_as_float(SA[4 * q + 3]), fmaf(-k2, __uint_as_float(SB[4 * q + 3]), fmaf(-ks, x23.y, k2 * t4.w)));
+                    }
+                    if (fix) {                                         // (rare; a branch, not predicated instructions)
+                        if (addlead) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
                                 const float4 l4 = *reinterpret_cast<const float4 *>(TOTl + 4 * q);
-                                v.x += l4.x; v.y += l4.y; v.z += l4.z; v.w += l4.w;
+                                v[q].x += l4.x; v[q].y += l4.y; v[q].z += l4.z; v[q].w += l4.w;
                             }
                         }
-                        st_hint4(rv + q, v, pol_keep);
+                        __syncwarp(__activemask());
                     }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) st_hint4(rv + q, v[q], pol_keep);
                     st_hint2(reinterpret_cast<float2 *>(a.recDM + (my_node * 2 + sl) * 2 * H_ + 2 * head), make_float2(den, M), pol_keep);
                 }
             }
