@@ -37,17 +37,26 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--n', type=int, default=100, help='cities per instance')
-    ap.add_argument('--instances-per-gpu', type=int, default=12500,
-                    help='shard per GPU; 12,500 x 8 GPUs = the 100k-instance TSP100 config of BASELINE.json')
+    ap.add_argument('--global-instances', type=int, default=100000,
+                    help='instances of the whole job, sharded over the ranks (strong scaling): the 100k-instance TSP100 '
+                         'config of BASELINE.json')
+    ap.add_argument('--instances-per-gpu', type=int, default=0,
+                    help='fixed shard per GPU instead (weak scaling); 0 = --global-instances / world size')
     ap.add_argument('--gls-iters', type=int, default=10, help='GLS outer iterations K (fixed count, SURVEY 8(d))')
     ap.add_argument('--perturbation-moves', type=int, default=20)
     ap.add_argument('--micro-batch', type=int, default=256)
     ap.add_argument('--chunk', type=int, default=2048, help='instances per host->device chunk in the e2e path')
-    ap.add_argument('--cpu-sample', type=int, default=4, help='instances in the bounded CPU-baseline sample')
-    ap.add_argument('--ref-sample', type=int, default=2, help='instances per step of the reference arm')
+    ap.add_argument('--cpu-sample', type=int, default=16, help='instances in the bounded CPU-baseline sample (all cores)')
+    ap.add_argument('--cpu-sample-1core', type=int, default=2, help='instances timed on ONE host core')
+    ap.add_argument('--ref-sample', type=int, default=16, help='instances per step of the reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    return ap.parse_args()
+    a = ap.parse_args()
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    a.scaling = 'weak' if a.instances_per_gpu > 0 else 'strong'
+    if a.instances_per_gpu <= 0:
+        a.instances_per_gpu = max(1, a.global_instances // world)
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -139,7 +148,7 @@ def cpu_calibrated_scalers(port, n):
     return s.calibrated(y)
 
 
-def cpu_reference_pass(port, D, n_iters, pm, threads, s):
+def cpu_reference_pass(port, D, n_iters, pm, threads, s, want_regret=False):
     """The reference's test.py:72-95 flow on CPU via the oracle: torch-CPU model (all threads) then the
     C port of nearest_neighbor + guided_local_search across `threads` host threads."""
     from gnngls_b200 import instances
@@ -155,7 +164,8 @@ def cpu_reference_pass(port, D, n_iters, pm, threads, s):
             y = port(g, torch.from_numpy(x[b]).reshape(-1, 1)).numpy().reshape(-1)
             r = ((y.astype(np.float64) - s.regret_min).astype(np.float32).astype(np.float64) / s.regret_scale).astype(np.float32)
             regret[b] = np.maximum(r, 0)
-    return gls_port.pipeline_batch(D, regret, n_iters, pm, nthreads=threads)
+    out = gls_port.pipeline_batch(D, regret, n_iters, pm, nthreads=threads)
+    return out + (regret,) if want_regret else out
 
 
 def run_reference(args, rank, world):
@@ -178,7 +188,7 @@ def run_reference(args, rank, world):
     value = args.ref_sample * args.steps / dt
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': args.scaling,
         'vs_baseline': None, 'dtype': 'fp32 (model) / fp64 (search)', 'data': 'synthetic',
         'config': workload_config(args, world),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
@@ -294,32 +304,44 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline of the dominant kernel: the GAT aggregate (K_n star + combine)
+    # ---------------- roofline of the dominant kernel: the K_n GAT aggregate (one launch per layer and micro-batch)
+    # achieved = ALGORITHMIC bytes / measured kernel time, with the algorithmic bytes of DESIGN.md section 5: every node of the
+    # line graph once -- fp16 ft 256 B + el/er 64 B + skip row h 512 B read, h1 512 B written = 1,344 B per node and layer.
+    # (SURVEY 8(d)'s 544 B per EDGE counts the 2(n-2)-fold logical gather that the star formulation serves from shared /
+    # tensor memory; it is reported as `logical_gather_gbs`, never as a fraction of the HBM peak.)
     N_nodes, E = n * (n - 1) // 2, n * (n - 1) * (n - 2)
     gat_ms, gat_calls = stages.get('gat_kn', stages.get('gat_csr', (0.0, 0)))
     per_call_instances = min(args.micro_batch, S)
-    alg_bytes_per_instance_layer = E * 544 + N_nodes * 544            # 544 B/edge + 544 B/node
+    node_bytes = 256 + 2 * 32 + 512 + 512
     peak, peak_src = peaks()
     roof = None
     if gat_calls:
-        # every timed call covers <= micro_batch instances; total instance-layers = steps * S * 8
-        total_bytes = alg_bytes_per_instance_layer * S * 8 * args.steps
-        achieved = total_bytes / (gat_ms / 1e3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, 'profiles', 'gat_kn_star_traffic.json')      # from the committed ncu --set full capture
+        inst_layers = S * 8 * args.steps
+        achieved = N_nodes * node_bytes * inst_layers / (gat_ms / 1e3) / 1e9
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, 'profiles', 'gat_kn_traffic.json')          # written by tools/ncu_traffic.py from an ncu --set full capture
         if os.path.exists(tp):
-            traffic = json.load(open(tp))['dram_bytes_per_instance_layer'] * per_call_instances
-        roof = {'kernel': 'gat_kn_star_f16_fused_kernel (K_n edge-softmax/aggregate + skip + BN1, one launch per layer and micro-batch)',
+            t = json.load(open(tp))
+            if t.get('kernel') == 'gat_kn_tc_kernel' and t.get('n') == n:
+                traffic = t['dram_bytes_per_instance_layer'] * per_call_instances
+                traffic_src = t.get('source')
+        roof = {'kernel': 'gat_kn_tc_kernel (K_n edge-softmax/aggregate + skip + BN1 on tcgen05)',
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic, 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': alg_bytes_per_instance_layer * per_call_instances,
+                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': N_nodes * node_bytes * per_call_instances,
                 'avg_launch_ms': gat_ms / gat_calls, 'launches_timed': gat_calls,
-                'compulsory_hbm_gbs': (N_nodes * (256 + 2 * 32 + 512 + 512) * S * 8 * args.steps) / (gat_ms / 1e3) / 1e9,
-                'note': 'achieved = ALGORITHMIC gather bytes of SURVEY 8(d) (544 B/edge + 544 B/node) / kernel time. The '
-                        'star kernel stages each ft row in shared memory once per incident vertex (2 reads per row) and '
-                        'serves the 2(n-2)=196-fold logical re-reads from SMEM/registers, so frac > 1 measures reuse, not '
-                        'skipped work; `traffic` is the real DRAM traffic per launch from ncu (DESIGN.md section 5); compulsory_hbm_gbs '
-                        'counts each node once: fp16 ft 256 B + el/er 64 B + skip h 512 B + h1 512 B.'}
+                'logical_gather_gbs': (E * 544 + N_nodes * 544) * inst_layers / (gat_ms / 1e3) / 1e9,
+                'limiter': 'latency / instruction issue, not HBM (profiles/r2_kn_tc.md): the HBM fraction says how far the '
+                           'kernel is from the only roofline that bounds its compulsory traffic'}
+    # the other model kernels against the same HBM peak (compulsory bytes per node and layer / measured stage time)
+    other = {}
+    for name, nbytes, nlaunch in (('fc', 256 + 256 + 64, 8), ('ff', 512 + 512 + 256, 8)):
+        ms_k, calls = stages.get(name, (0.0, 0))
+        if calls:
+            gbs = N_nodes * nbytes * S * nlaunch * args.steps / (ms_k / 1e3) / 1e9
+            other[name] = {'bound': 'hbm', 'achieved': gbs, 'frac': gbs / peak, 'unit': 'GB/s', 'bytes_per_node': nbytes}
+    if roof is not None:
+        roof['other_kernels'] = other
     total_stage = sum(v[0] for v in stages.values())
     stage_ms = {k: round(v[0] / args.steps, 3) for k, v in stages.items()}
     cand_2opt, cand_rel = (n - 2) * (n - 3) // 2, (n - 2) ** 2
@@ -333,22 +355,35 @@ def main():
         from oracle import gls_port
         gls_port.build()
         threads = os.cpu_count() or 1
-        torch.set_num_threads(threads)
         port = make_port_model()
         sample = min(args.cpu_sample, S)
+        torch.set_num_threads(threads)
         t0 = time.perf_counter()
-        o_t, o_c = cpu_reference_pass(port, D_np[:sample], args.gls_iters, args.perturbation_moves, threads,
-                                      solver.scalers)
+        o_t, o_c = cpu_reference_pass(port, D_np[:sample], args.gls_iters, args.perturbation_moves, threads, solver.scalers)
         dt = time.perf_counter() - t0
+        s1 = min(args.cpu_sample_1core, sample)
+        torch.set_num_threads(1)
+        t0 = time.perf_counter()
+        cpu_reference_pass(port, D_np[:s1], args.gls_iters, args.perturbation_moves, 1, solver.scalers)
+        dt1 = time.perf_counter() - t0
+        torch.set_num_threads(threads)
+        g_c = res.best_costs[:sample].cpu().numpy()
+        d = g_c - o_c                                   # paired: same instances, each side with its own predicted regrets
+        half = 1.96 * float(d.std(ddof=1)) / np.sqrt(sample) if sample > 1 else float('nan')
         cpu = {'value': sample / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'sample': f'first {sample} instances of the same workload, {dt:.1f} s: oracle torch-CPU model + C port '
+               'sample': f'first {sample} instances of the same workload, {dt:.1f} s: oracle torch-CPU model ({threads} threads) + C port '
                          f'of nearest_neighbor/GLS (K={args.gls_iters})',
-               'best_cost_mean_cpu': float(o_c.mean()),
-               'best_cost_mean_gpu_same_instances': float(res.best_costs[:sample].mean())}
+               'single_core': {'value': s1 / dt1, 'unit': UNIT, 'cores': 1, 'sample': f'first {s1} instances, {dt1:.1f} s'},
+               'best_cost_mean_cpu': float(o_c.mean()), 'best_cost_mean_gpu_same_instances': float(g_c.mean()),
+               'best_cost_paired_diff': {'mean_gpu_minus_cpu': float(d.mean()), 'ci95_halfwidth': half,
+                                         'relative_to_cpu_mean': float(d.mean() / o_c.mean()), 'pairs': sample,
+                                         'note': 'random-init weights: the guide is noise, near-ties flip between the fp32 CPU '
+                                                 'model and the tensor-core model; identical regrets give identical tours '
+                                                 '(tests/test_model_gpu.py)'}}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'fp16 operands (10-bit mantissa, as TF32) with fp32 accumulate for the GNN contractions, fp32 elsewhere + fp64 (search)', 'data': 'synthetic',
         'config': dict(workload_config(args, world), weights=weights),
         'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu,

@@ -97,10 +97,20 @@ def load():
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.exists(path):
-        try:
-            _build.build()
-        except Exception as e:  # noqa: BLE001
+    # build() is incremental (mtime of every source and header against its object), so a stale library never survives an
+    # edit of csrc/ or the header; the lock keeps the ranks of one torchrun from compiling into the same files at once.
+    # Without nvcc (a box that only received the built library) the existing .so is used as it is.
+    try:
+        import fcntl
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path + '.lock', 'w') as lk:
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            try:
+                _build.build()
+            finally:
+                fcntl.flock(lk, fcntl.LOCK_UN)
+    except Exception as e:  # noqa: BLE001
+        if not os.path.exists(path):
             raise RuntimeError(
                 f'libgnngls_b200.so is missing and could not be built ({e}); gnngls_b200 has no CPU fallback. '
                 'Run `python -m gnngls_b200.build`.') from e

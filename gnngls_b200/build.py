@@ -38,6 +38,30 @@ def nvcc():
     return path
 
 
+HASH_PATH = LIB_PATH + '.srchash'
+
+
+def source_hash():
+    """Content hash of everything the library is built from (sources, headers, flags): travels with the .so so that a
+    copy of the tree with different mtimes is not rebuilt, while an edited source always is."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.h', '.cuh')))
+    files.append(os.path.join(INCLUDE, 'gnngls_b200.h'))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, 'rb').read())
+    h.update(repr((ARCH, COMMON[:3], sorted(SOURCES.items()))).encode())
+    return h.hexdigest()
+
+
+def up_to_date():
+    try:
+        return os.path.exists(LIB_PATH) and open(HASH_PATH).read().strip() == source_hash()
+    except OSError:
+        return False
+
+
 def _stale(target, deps):
     if not os.path.exists(target):
         return True
@@ -47,6 +71,8 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OUT_DIR, exist_ok=True)
+    if not force and up_to_date():
+        return LIB_PATH
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
     headers += [os.path.join(INCLUDE, 'gnngls_b200.h'), os.path.abspath(__file__)]
     jobs, objs = [], []
@@ -73,7 +99,10 @@ def build(force=False, verbose=False):
                 if verbose and warn.strip():
                     print(warn)
     if force or jobs or _stale(LIB_PATH, objs):
-        run([nvcc()] + ARCH + ['-shared', '-o', LIB_PATH] + objs)
+        run([nvcc()] + ARCH + ['-shared', '-o', LIB_PATH + '.tmp'] + objs)
+        os.replace(LIB_PATH + '.tmp', LIB_PATH)             # atomic: a concurrent loader never sees a half-written file
+    with open(HASH_PATH, 'w') as f:
+        f.write(source_hash())
     return LIB_PATH
 
 

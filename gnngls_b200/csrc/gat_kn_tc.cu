@@ -207,25 +207,26 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
     }
     __syncthreads();
     int cur = SI[0], nxt = SI[1];                                      // star slots are handed out in order, one star ahead
-    int mcur = -1, mpend = -1;                                         // merge slice of this iteration / taken but its instance not complete yet
+    int cand = -1;                                                     // merge slice taken by this CTA, not merged yet (-1: none)
     __syncthreads();
     if (cur < total) issue_scores(cur / n, cur % n, 0);
     cp_async_commit();
     uint32_t parity = 0;
 
-    for (int it = 0; cur < total || mcur >= 0 || mpend >= 0; ++it) {
+    for (int it = 0; cur < total || cand >= 0 || it == 0; ++it) {
         const int b = cur / n, i = cur - b * n, cbuf = it & 1;
         const bool havestar = cur < total;
-        // Merge slices (instance bm, nodes [mlo, mhi)) are handed out in order too, but a CTA only merges a slice once all n stars of
-        // its instance are out; until then it keeps the slice and carries on with its stars.  Nothing a star does waits for a merge.
-        const bool havemerge = mcur >= 0;
-        const int bm = havemerge ? mcur / n : 0, im = mcur - bm * n;
-        const int mlo = (im * (n - 1)) >> 1, mhi = havemerge ? ((im + 1) * (n - 1)) >> 1 : 0;
-        const size_t mnode0 = (size_t)bm * N;
-        int grabbed = 0, mtake = -1;
+        int grabbed = 0;
         if (tid == 0) {
             grabbed = atomicAdd(ctr, 1);                               // the slot after next (needed at the end of the iteration)
-            if (mpend < 0) mtake = atomicAdd(mctr, 1);                 // the slice to merge in the next iteration
+            // Merge slices (instance bm, nodes [mlo, mhi)) are handed out in order too, but a CTA only merges its slice once all n
+            // stars of that instance are out: a look at the top of every iteration, never a wait while a star is pending.
+            int rdy = 0;
+            if (cand >= 0) {
+                rdy = ld_acquire_gpu(a.flags + cand / n) >= n;
+                if (!rdy && !havestar) __nanosleep(1000);              // (only merging left: do not hammer the counter)
+            }
+            SI[2] = rdy;
         }
         // this thread as member / destination row tt of the current star; its features for the first head
         const bool live = havestar && tt < n && tt != i;
@@ -234,13 +235,20 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         const uint4 *ftrow = reinterpret_cast<const uint4 *>(static_cast<const unsigned char *>(a.ft) + my_node * 256);
         uint4 f0 = make_uint4(0u, 0u, 0u, 0u), f1 = f0;
         if (live) { f0 = __ldg(ftrow); f1 = __ldg(ftrow + 1); }
+        cp_async_wait_group<0>();                                      // the current star's scores (requested a star ago)
+        __syncthreads();
+        const int mcur = SI[2] ? cand : -1;                            // the slice merged in this iteration
+        const bool havemerge = mcur >= 0;
+        const int bm = havemerge ? mcur / n : 0, im = mcur - bm * n;
+        const int mlo = (im * (n - 1)) >> 1, mhi = havemerge ? ((im + 1) * (n - 1)) >> 1 : 0;
+        const size_t mnode0 = (size_t)bm * N;
+        int mtake = cand;
+        if (tid == 0 && (havemerge || cand < 0)) mtake = atomicAdd(mctr, 1);   // the next slice (needed at the end of the iteration)
         if (havemerge) {
-            // skip rows of the merge slice: bring them into L2 now, they are fetched one MMA shadow before they are used
+            // skip rows of the merge slice: start them on their way into L2, they are fetched one MMA shadow before they are used
             for (int idx = tid; idx < (mhi - mlo) * 4; idx += T_THREADS)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h + (mnode0 + mlo) * D_ + 32 * idx));
         }
-        cp_async_wait_group<0>();                                      // the current star's scores (requested a star ago)
-        __syncthreads();
         if (nxt < total) issue_scores(nxt / n, nxt % n, cbuf ^ 1);
         // merge rows of MMA shadow `hs` (this warp: rows mlo + 4 hs + warp, + 32): records of both stars and skip row -> shared memory
         auto fetch_merge_rows = [&](int hs) {
@@ -483,14 +491,8 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
             }
         }
         if (tid == 0) {
-            int cand = mpend >= 0 ? mpend : mtake;
-            if (cand >= total) cand = -1;                              // no slices left
-            int rdy = 0;
-            if (cand >= 0) {
-                rdy = ld_acquire_gpu(a.flags + cand / n) >= n;         // a look, not a wait
-                if (!rdy && !havestar) __nanosleep(1000);              // (only merging left: do not hammer the counter)
-            }
-            SI[0] = grabbed; SI[1] = cand; SI[2] = rdy;
+            SI[0] = grabbed;
+            SI[1] = mtake >= total ? -1 : mtake;                       // (no slices left)
         }
         __syncthreads();                                               // this star's records are all written; next slot / slice known
         if (havestar && tid == 0) {
@@ -499,8 +501,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         }
         cur = nxt;
         nxt = SI[0];
-        mcur = SI[2] ? SI[1] : -1;
-        mpend = SI[2] ? -1 : SI[1];
+        cand = SI[1];
         __syncthreads();                                               // (SI is rewritten in the next iteration)
     }
     // ---------------------------------------------------------------- teardown

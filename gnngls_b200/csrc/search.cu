@@ -30,6 +30,7 @@ struct Best {
 // numpy.isclose(0, d): |0 - d| <= atol + rtol * |d|  (operators.py:42)
 __device__ __forceinline__ bool close_to_zero(double d) {
     const double ad = fabs(d);
+    if (!(ad < INFINITY)) return false;                 // np.isclose(0, +-inf) and np.isclose(0, nan) are False
     return ad <= __dadd_rn(1e-8, __dmul_rn(1e-5, ad));
 }
 
@@ -354,6 +355,16 @@ __global__ void moves_kernel(int op, bool o2a, const double *Dg, int64_t d_strid
         int i_fixed = 0;
         if (o2a) {
             i_fixed = pos[b];
+            // the reference asserts 0 < i < len(tour) - 1 (operators.py:107,129); a position outside that range reads
+            // t[i-1] / t[i+1] out of bounds, so it is reported as "no move" with position -2 instead
+            if (i_fixed < 1 || i_fixed > n - 1) {
+                best.delta = 0.0; best.key = -1; best.pad = 0;
+                if (threadIdx.x == 0) { out_delta[b] = 0.0; out_move[2 * b] = -2; out_move[2 * b + 1] = -2; }
+                if (out_tours)
+                    for (int p = threadIdx.x; p <= n; p += blockDim.x) out_tours[(size_t)b * (n + 1) + p] = s.tour[p];
+                __syncthreads();
+                continue;
+            }
             best = (op == GNNGLS_OP_TWO_OPT) ? scan_two_opt_o2a(s.tour, n, D, i_fixed, fi != 0, s.red)
                                              : scan_relocate_o2a(s.tour, n, D, i_fixed, fi != 0, s.red);
         } else {

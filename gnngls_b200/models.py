@@ -72,6 +72,14 @@ class GATConv(nn.Module):
 
     def forward(self, G, feat):
         M = G.number_of_nodes()
+        if not feat.is_cuda:
+            raise RuntimeError('gnngls_b200 has no CPU path: move the layer, graph and features to a CUDA device')
+        if feat.dim() != 2 or tuple(feat.shape) != (M, self._in_feats) or self._in_feats != 128:
+            raise RuntimeError(f'GATConv expects [{M}, 128] features; got {tuple(feat.shape)}')
+        with torch.cuda.device(feat.device):                  # launches go to the stream of the tensor's device
+            return self._forward(G, feat, M)
+
+    def _forward(self, G, feat, M):
         zero = torch.zeros(M, self._in_feats, dtype=torch.float32, device=feat.device)
         one = torch.ones(self._in_feats, dtype=torch.float32, device=feat.device)
         tc = _dense_impl_default() != 'simt'
@@ -95,9 +103,14 @@ def tf32_round(t):
 _KN_MAX_N = 1024      # largest vertex star the K_n kernel holds in one CTA's shared memory (csrc/gat_kn.cu)
 
 
+_OPERAND_OVERRIDE = []      # innermost EdgePropertyPredictionModel.operand_dtype while its forward runs
+
+
 def _op_f16():
-    """Tensor-core path: operand copies / weights travel as fp16 unless GNNGLS_OP_DTYPE=tf32 (or the older
-    GNNGLS_FF_DTYPE=tf32) asks for the all-TF32 kernels."""
+    """Tensor-core path: operand copies / weights travel as fp16 unless the model's `operand_dtype` attribute,
+    GNNGLS_OP_DTYPE=tf32 (or the older GNNGLS_FF_DTYPE=tf32) asks for the all-TF32 kernels."""
+    if _OPERAND_OVERRIDE and _OPERAND_OVERRIDE[-1] is not None:
+        return _OPERAND_OVERRIDE[-1] != 'tf32'
     return (os.environ.get('GNNGLS_OP_DTYPE', 'f16').lower() != 'tf32'
             and os.environ.get('GNNGLS_FF_DTYPE', 'f16').lower() != 'tf32')
 
@@ -132,7 +145,7 @@ def _gat_block(G, h_op, skip, Wfc, al, ar, bias, bn_scale, bn_shift, dense_impl,
     # bytes); GNNGLS_FT_DTYPE=tf32 keeps fp32 storage.  The fp32 debug path keeps ft exact.
     if not tc:
         ft_dtype = _ops.FT_F32
-    elif os.environ.get('GNNGLS_FT_DTYPE', 'f16').lower() == 'tf32':
+    elif os.environ.get('GNNGLS_FT_DTYPE', 'f16').lower() == 'tf32' or (_OPERAND_OVERRIDE and _OPERAND_OVERRIDE[-1] == 'tf32'):
         ft_dtype = _ops.FT_TF32
     else:
         ft_dtype = _ops.FT_F16
@@ -197,6 +210,16 @@ class AttentionLayer(nn.Module):
             raise NotImplementedError('gnngls_b200 implements the inference path only: call model.eval()')
         if self._dims != (128, 8, 512):
             raise NotImplementedError('kernels are specialised for embed_dim=128, n_heads=8, hidden_dim=512')
+        if not x.is_cuda:
+            raise RuntimeError('gnngls_b200 has no CPU path: move the layer, graph and features to a CUDA device')
+        if x.dim() != 2 or x.shape[1] != 128:
+            raise RuntimeError(f'AttentionLayer expects [nodes, 128] features; got {tuple(x.shape)}')
+        if x.shape[0] != G.number_of_nodes():
+            raise ValueError(f'features have {x.shape[0]} rows but the graph has {G.number_of_nodes()} nodes')
+        with torch.cuda.device(x.device):                      # launches go to the stream of the tensor's device
+            return self._forward(G, x, _params, _ws, _dense_impl, _gat_impl, _out, _x_tf32, _out_tf32)
+
+    def _forward(self, G, x, _params, _ws, _dense_impl, _gat_impl, _out, _x_tf32, _out_tf32):
         lib = _lib.load()
         prm = _params if _params is not None else self._device_params()
         ws = _ws if _ws is not None else {}
@@ -204,7 +227,7 @@ class AttentionLayer(nn.Module):
             _ops.DENSE_SIMT if _dense_impl_default() == 'simt' else _ops.DENSE_TCGEN05)
         tc = impl == _ops.DENSE_TCGEN05
         f16 = tc and _op_f16()
-        x = x.contiguous()
+        x = x.detach().to(torch.float32).contiguous()
         M, dev = x.shape[0], x.device
         sfx = '_f16' if f16 else ('_tf32' if tc else '')
         op_impl = _ops.DENSE_TCGEN05_F16 if f16 else impl
@@ -237,6 +260,10 @@ class EdgePropertyPredictionModel(nn.Module):
         self.decision_layer = nn.Linear(embed_dim, out_dim)
         self.dense_impl = None      # None -> $GNNGLS_DENSE_IMPL or 'tcgen05'
         self.gat_impl = 'auto'      # 'auto' | 'kn' | 'csr'
+        # operands of the tensor-core contractions: None -> $GNNGLS_OP_DTYPE or 'f16'; 'tf32' = the wide-exponent mode for
+        # checkpoints whose activations leave fp16's range (|h| > 65504 saturates, |h| < 6e-5 loses bits); feature storage
+        # becomes fp32 too and the K_n aggregate runs its exact fp32 sorted-prefix kernel
+        self.operand_dtype = None
         self._cache_sig, self._cache = None, None
         self._ws = {}
 
@@ -267,11 +294,23 @@ class EdgePropertyPredictionModel(nn.Module):
         prm = self._prepared()
         name = self.dense_impl or _dense_impl_default()
         impl = _ops.DENSE_SIMT if name == 'simt' else _ops.DENSE_TCGEN05
+        in_dim, out_dim = self.embed_layer.in_features, self.decision_layer.out_features
+        if x.dim() != 2 or x.shape[1] != in_dim:              # what nn.Linear would raise; the kernel indexes x[m * in_dim + k]
+            raise RuntimeError(f'features must be [nodes, {in_dim}] (embed_layer.in_features); got {tuple(x.shape)}')
         x = x.detach().to(torch.float32).contiguous()
         M, dev = x.shape[0], x.device
         if M != G.number_of_nodes():
             raise ValueError(f'features have {M} rows but the graph has {G.number_of_nodes()} nodes')
-        in_dim, out_dim = self.embed_layer.in_features, self.decision_layer.out_features
+        p = _ops._ptr
+        if self.operand_dtype not in (None, 'f16', 'tf32'):
+            raise ValueError("operand_dtype must be None, 'f16' or 'tf32'")
+        _OPERAND_OVERRIDE.append(self.operand_dtype)
+        try:
+            return self._forward_impl(G, x, lib, prm, impl, M, dev, in_dim, out_dim)
+        finally:
+            _OPERAND_OVERRIDE.pop()
+
+    def _forward_impl(self, G, x, lib, prm, impl, M, dev, in_dim, out_dim):
         p = _ops._ptr
         with torch.cuda.device(dev):
             tc = impl == _ops.DENSE_TCGEN05

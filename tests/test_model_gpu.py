@@ -379,4 +379,78 @@ def test_large_n_kn_kernel_vs_fp64_rows(n, ft_dtype):
     rows = np.unique(np.concatenate([rng.integers(0, M, 380), hot[:20].numpy(), [0, N - 1, M - 1]]))
     ref = _kn_ref.aggregate_rows(n, rows, ft.float().numpy(), el.numpy(), er.numpy(), h.numpy(), bias.numpy(), sc.numpy(), sh.numpy())
     err = np.abs(out.numpy()[rows].astype(np.float64) - ref).max()
-    assert err < 3e-5 * float(ft.abs().max()), (n, err)
+    # n <= 128 with fp16 storage runs the tcgen05 kernel (operand rows rounded to fp16); everything else is fp32 arithmetic
+    tol = (1.5e-3 if (f16 and n <= 128) else 3e-5) * float(ft.abs().max())
+    assert err < tol, (n, err, tol)
+
+
+def test_operand_range_fp16_vs_tf32_mode():
+    """fp16 operands share TF32's 10-bit mantissa but not its exponent: activations above 65504 saturate and activations
+    below 6e-5 lose mantissa bits.  Scale the embedding so that the residual stream sits (a) far above and (b) far below
+    fp16's range: `operand_dtype='tf32'` (wide exponent, fp32 feature storage, exact K_n kernel) must stay inside the TF32
+    budget in both cases; the default fp16 mode must stay finite, and is expected to leave the budget -- which is the
+    documented reason the mode exists (README / INTEGRATION.md)."""
+    n, B = 12, 2
+    N = n * (n - 1) // 2
+    x = np.random.default_rng(3).random((B * N, 1)).astype(np.float32)
+    for scale, label in ((3e5, 'above fp16 range'), (1e-6, 'below fp16 normal range')):
+        port, m = make_models()
+        with torch.no_grad():                                   # eval-mode BN with running stats is affine: the scale survives
+            port.embed_layer.weight.mul_(scale); port.embed_layer.bias.mul_(scale)
+            for l in port.message_passing_layers:               # keep the attention logits O(1) so the softmax stays informative
+                l.message_passing.module.attn_l.div_(scale); l.message_passing.module.attn_r.div_(scale)
+        m.load_state_dict(port.state_dict(), strict=True)
+        with torch.no_grad():
+            y64 = port.double()(model_port.EdgeListGraph.kn_line_graph(n, B), torch.as_tensor(x).double()).numpy()
+        port.float()
+        tol = tf32_budget(port, n, B, x, y64)
+        m.operand_dtype = 'tf32'
+        e_tf32 = np.abs(run(m, n, B, x, 'tcgen05', 'kn') - y64).max()
+        m.operand_dtype = 'f16'
+        y16 = run(m, n, B, x, 'tcgen05', 'kn')
+        e_f16 = np.abs(y16 - y64).max()
+        print(f'{label}: |y|max={np.abs(y64).max():.3e} tol={tol:.3e} err tf32 mode={e_tf32:.3e} fp16 mode={e_f16:.3e}')
+        assert e_tf32 <= tol, (label, e_tf32, tol)
+        assert np.isfinite(y16).all(), label
+
+
+@pytest.mark.parametrize('n,B,mode', [(20, 100, 'f16'), (20, 100, 'tf32'), (50, 48, 'f16'), (100, 24, 'f16'), (100, 24, 'tf32')])
+def test_optimality_statistically_unchanged(n, B, mode):
+    """North-star correctness leg 3 (/root/reference/scripts/test.py:59-104): the same instances solved end to end on the CPU
+    (oracle: fp32 torch model + C port of nearest_neighbor / guided_local_search) and on the GPU, EACH SIDE WITH ITS OWN
+    predicted regrets.  Tours differ where near-ties of the (random-init, i.e. noise) guide flip; the best costs must be
+    statistically indistinguishable: |mean paired difference| <= 3 standard errors, or below 0.1 % of the mean cost."""
+    from gnngls_b200 import pipeline
+    from oracle import gls_port
+    gls_port.build()
+    torch.manual_seed(0)
+    port = model_port.EdgeModelPort(1, 128, 1, 3, n_heads=8).eval()
+    m = models.EdgePropertyPredictionModel(1, 128, 1, 3, n_heads=8)
+    m.load_state_dict(port.state_dict(), strict=True)
+    m = m.cuda().eval()
+    m.operand_dtype = mode
+    solver = pipeline.RegretGLS(m, micro_batch=64)
+    _, D = instances.random_instances(B, n, seed=77)
+    _, Dcal = instances.random_instances(8, n, seed=76)
+    s = solver.calibrate_synthetic_regret_scaler(torch.from_numpy(Dcal).cuda())
+    K, pm = 10, 20
+    res = solver.solve(torch.from_numpy(D).cuda(), n_iters=K, perturbation_moves=pm)
+    g_cost = res.best_costs.cpu().numpy()
+    # CPU side: features -> oracle model -> inverse scale / clamp -> C port of the search, same scalers
+    x = instances.edge_features(D)
+    x = ((x.astype(np.float64) * s.feat_scale).astype(np.float32).astype(np.float64) + s.feat_min).astype(np.float32)
+    g1 = model_port.EdgeListGraph.kn_line_graph(n, 1)
+    regret = np.empty((B, n * (n - 1) // 2), dtype=np.float32)
+    with torch.no_grad():
+        for b in range(B):
+            y = port(g1, torch.from_numpy(x[b]).reshape(-1, 1)).numpy().reshape(-1)
+            r = ((y.astype(np.float64) - s.regret_min).astype(np.float32).astype(np.float64) / s.regret_scale).astype(np.float32)
+            regret[b] = np.maximum(r, 0)
+    import os
+    _, c_cost = gls_port.pipeline_batch(D, regret, K, pm, nthreads=os.cpu_count() or 1)
+    d = g_cost - c_cost
+    se = d.std(ddof=1) / np.sqrt(B)
+    rel = abs(d.mean()) / c_cost.mean()
+    print(f'TSP{n} x {B} [{mode}]: CPU mean {c_cost.mean():.5f} GPU mean {g_cost.mean():.5f} paired diff {d.mean():+.5f} '
+          f'+- {1.96 * se:.5f} (95 %), {100 * rel:.3f} % of the mean; identical tours costs: {(d == 0).mean():.2f}')
+    assert abs(d.mean()) <= 3 * se or rel < 1e-3, (n, B, mode, d.mean(), se)

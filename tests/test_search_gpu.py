@@ -160,17 +160,18 @@ def test_moves_eval_shared_matrix():
 
 
 @pytest.mark.parametrize('n,B,K', [(4, 8, 3), (10, 32, 6), (20, 64, 10), (50, 32, 6), (100, 24, 4), (130, 4, 2),
-                                   (170, 2, 1)])
+                                   (170, 2, 1), (500, 2, 1)])
 def test_nn_ls_gls_batch_vs_oracle(n, B, K):
     """Whole search pipeline (test.py:85-95) on a batch: NN init on an fp32 regret edge vector,
-    tour_cost, local_search, GLS — bit-exact vs the CPU oracle; n=170 exercises the global-memory tier."""
+    tour_cost, local_search, GLS — bit-exact vs the CPU oracle; n=170 exercises the global-memory tier, n=500 is
+    BASELINE.json's TSP500 configuration."""
     rng = np.random.default_rng(n)
     _, D = instances.random_instances(B, n, seed=7 * n)
     N = n * (n - 1) // 2
     regret = np.maximum(rng.random((B, N)).astype(np.float32) - np.float32(0.4), 0).astype(np.float32)
     Dd, rd = dev(D), dev(regret)
     tours, costs = algorithms.nearest_neighbor_batch(rd, Dd)
-    ls_t, ls_c, ls_info = algorithms.local_search_batch(tours, costs, Dd, max_events=512)
+    ls_t, ls_c, ls_info = algorithms.local_search_batch(tours, costs, Dd, max_events=2048)
     bt, bc, info = algorithms.guided_local_search_batch(Dd, rd.view(B, 1, N), tours, costs, K, perturbation_moves=20,
                                                         max_events=8192, keep_penalties=True)
     assert int(info['status'].max()) == 0
