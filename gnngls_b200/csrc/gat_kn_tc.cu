@@ -261,7 +261,9 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 const float *rv = a.recV + node * 2 * D_;
                 cp_async16_hint(dst + 4 * lane, rv + 4 * lane, pol_stream);
                 cp_async16_hint(dst + D_ + 4 * lane, rv + D_ + 4 * lane, pol_stream);
-                if (lane < 8) cp_async16_hint(dst + 2 * D_ + 4 * lane, a.recDM + node * 4 * H_ + 4 * lane, pol_stream);
+                // (all lanes: the cache-policy operand lives in a uniform register, which a divergent lane subset must not
+                // reload; lanes 8..31 repeat the pieces of lanes 0..7)
+                cp_async16_hint(dst + 2 * D_ + 4 * (lane & 7), a.recDM + node * 4 * H_ + 4 * (lane & 7), pol_stream);
                 cp_async16_hint(dst + 2 * D_ + 32 + 4 * lane, a.h + node * D_ + 4 * lane, pol_stream);
             }
         };
