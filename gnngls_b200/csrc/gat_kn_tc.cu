@@ -33,6 +33,22 @@
 // spread over the shadows of its eight MMA chains (one per head), the only places where its warps would otherwise wait.
 #include "gat_kn.cuh"
 
+// Phase timing (debug builds only: GNNGLS_KN_STAMPS=1 python -m gnngls_b200.build --force): lane 0 of every warp accumulates
+// clock64() differences per phase; read back with gnngls_debug_kn_stamps() (tools/kn_stamps.py).
+#ifdef KN_STAMPS
+__device__ unsigned long long g_kn_stamps[148 * 4 * 4 * 16];
+#define KN_STAMP(slot)                                              \
+    do {                                                            \
+        if (lane == 0) {                                            \
+            const long long now__ = clock64();                      \
+            stamp_acc[slot] += (unsigned long long)(now__ - stamp_last); \
+            stamp_last = now__;                                     \
+        }                                                           \
+    } while (0)
+#else
+#define KN_STAMP(slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int T_THREADS = 128, T_WARPS = 4, KPAD = 128;
@@ -108,6 +124,16 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 }
 __device__ __forceinline__ void st_hint4(float4 *p, float4 v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+// 256-bit global accesses: one full 32-byte sector per lane and instruction (a lane's 64-byte chunk of a record or of a feature
+// row costs half the LSU wavefronts of 128-bit accesses -- the L1 data pipe is this kernel's scarcest resource)
+__device__ __forceinline__ void st_keep8(float *p, float4 a, float4 b) {
+    asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)),
+                 "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)),
+                 "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w)) : "memory");
+}
+__device__ __forceinline__ void ldg8(const void *p, uint4 &a, uint4 &b) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
 __device__ __forceinline__ void st_hint2(float2 *p, float2 v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
@@ -211,6 +237,10 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
     __syncthreads();
     if (cur < total) issue_scores(cur / n, cur % n, 0);
     cp_async_commit();
+#ifdef KN_STAMPS
+    unsigned long long stamp_acc[16] = {};
+    long long stamp_last = clock64();
+#endif
     uint32_t parity = 0;
 
     for (int it = 0; cur < total || cand >= 0 || it == 0; ++it) {
@@ -234,9 +264,11 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         const size_t my_node = (size_t)b * N + my_local;
         const uint4 *ftrow = reinterpret_cast<const uint4 *>(static_cast<const unsigned char *>(a.ft) + my_node * 256);
         uint4 f0 = make_uint4(0u, 0u, 0u, 0u), f1 = f0;
-        if (live) { f0 = __ldg(ftrow); f1 = __ldg(ftrow + 1); }
+        if (live) ldg8(ftrow, f0, f1);
+        KN_STAMP(0);                                                   // top: bookkeeping, feature loads, readiness look
         cp_async_wait_group<0>();                                      // the current star's scores (requested a star ago)
         __syncthreads();
+        KN_STAMP(1);                                                   // scores + barrier
         const int mcur = SI[2] ? cand : -1;                            // the slice merged in this iteration
         const bool havemerge = mcur >= 0;
         const int bm = havemerge ? mcur / n : 0, im = mcur - bm * n;
@@ -298,7 +330,9 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 for (int q = 0; q < KPAD / 32; ++q) ELHall[head * KPAD + lane + 32 * q] = __float2half_rn(ev[q] - ref);
                 if (lane == 0) *reinterpret_cast<float4 *>(HD + head * 4) = make_float4(ref, t2.m1, __int_as_float(t2.a1), __int_as_float(fix ? 1 : 0));
             }
+            KN_STAMP(2);                                               // slice setup, top-2
             __syncthreads();
+            KN_STAMP(3);                                               // barrier
         }
 
         // the merge rows fetched one shadow ago: combine the two stars' records in fixed (lower, higher) order, apply bias + skip +
@@ -308,6 +342,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
             const float4 bb4 = a.bias ? __ldg(reinterpret_cast<const float4 *>(a.bias) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
             cp_async_wait_group<0>();
             __syncwarp();
+            KN_STAMP(15);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int r = mlo + hs * T_WARPS + warp + 32 * q;
@@ -384,7 +419,8 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                     }
                     __syncwarp();
                 }
-                if (live && head + 1 < H_) { f0 = __ldg(ftrow + 2 * (head + 1)); f1 = __ldg(ftrow + 2 * (head + 1) + 1); }   // next head's features
+                KN_STAMP(14);
+                if (live && head + 1 < H_) ldg8(ftrow + 2 * (head + 1), f0, f1);   // next head's features
                 // ---- indicator row of destination tt: I[tt][k] = [el_k - ref >= -er_tt - ref] as fp16 1.0 / 0.0, straight into tensor
                 // memory.  Row i (the vertex itself, not a destination) takes threshold -inf: its accumulator row is the column totals.
                 {
@@ -405,10 +441,13 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                         tmem_st16(tbase + lane_sel + c * 16, v);
                     }
                 }
+                KN_STAMP(4);                                           // operand row + indicator
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // B operand written through the generic proxy
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                KN_STAMP(5);                                           // wait::st + fences
                 __syncthreads();                                       // operands complete
+                KN_STAMP(6);                                           // barrier A
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tid == 0) {
                     for (int ks = 0; ks < nk; ++ks)
@@ -417,12 +456,15 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 }
                 __syncwarp();
             }
+            KN_STAMP(7);                                               // MMA issue
             if (havemerge) merge_rows(head);                           // in the shadow of the MMA chain
+            KN_STAMP(8);                                               // merge rows
             if (havestar) {
                 // ---- accumulators
                 uint32_t SA[16], SB[16], SD0, SD1;
                 mbar_wait(bar, parity);
                 parity ^= 1;
+                KN_STAMP(9);                                           // rest of the MMA
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 tmem_ld16(tbase + lane_sel + 64, SA);
                 tmem_ld16(tbase + lane_sel + 80, SB);
@@ -435,7 +477,9 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                         *reinterpret_cast<uint4 *>(TOT + 4 * q) = make_uint4(SB[4 * q], SB[4 * q + 1], SB[4 * q + 2], SB[4 * q + 3]);
                     TOT[16] = __uint_as_float(SD1);
                 }
+                KN_STAMP(10);                                          // accumulators -> registers
                 __syncthreads();                                       // totals visible; every row has its accumulators
+                KN_STAMP(11);                                          // barrier B
                 if (live) {
                     // ---- this star's partial for destination tt (fp32): v = C1 SA + C2 (Tot - SB) - self (+ leading member)
                     const float4 hd = *reinterpret_cast<const float4 *>(HD + head * 4);
@@ -486,12 +530,14 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                         }
                         __syncwarp(__activemask());
                     }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) st_hint4(rv + q, v[q], pol_keep);
+                    st_keep8(reinterpret_cast<float *>(rv), v[0], v[1]);
+                    st_keep8(reinterpret_cast<float *>(rv + 2), v[2], v[3]);
                     st_hint2(reinterpret_cast<float2 *>(a.recDM + (my_node * 2 + sl) * 2 * H_ + 2 * head), make_float2(den, M), pol_keep);
                 }
+                KN_STAMP(12);                                          // partial
             }
         }
+        KN_STAMP(12);                                                  // (last) partial
         if (tid == 0) {
             SI[0] = grabbed;
             SI[1] = mtake >= total ? -1 : mtake;                       // (no slices left)
@@ -505,7 +551,12 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         nxt = SI[0];
         cand = SI[1];
         __syncthreads();                                               // (SI is rewritten in the next iteration)
+        KN_STAMP(13);                                                  // end of star: barriers, publish
     }
+#ifdef KN_STAMPS
+    if (lane == 0 && blockIdx.x < 148 * 4)
+        for (int k = 0; k < 16; ++k) g_kn_stamps[(blockIdx.x * 4 + warp) * 16 + k] = stamp_acc[k];
+#endif
     // ---------------------------------------------------------------- teardown
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -541,3 +592,15 @@ int launch_kn_tc(const KnArgs &args_in, int B, void *workspace, cudaStream_t st)
     return GNNGLS_OK;
 }
 }  // namespace gnngls
+
+// debug: per-(CTA, warp) phase cycle totals of the last launch (error unless built with -DKN_STAMPS)
+extern "C" int gnngls_debug_kn_stamps(unsigned long long *out, int count) {
+#ifdef KN_STAMPS
+    if (count > 148 * 4 * 4 * 16) count = 148 * 4 * 4 * 16;
+    GNNGLS_CUDA_OK(cudaMemcpyFromSymbol(out, g_kn_stamps, sizeof(unsigned long long) * count));
+    return GNNGLS_OK;
+#else
+    (void)out; (void)count;
+    return GNNGLS_ERR_UNSUPPORTED;
+#endif
+}
