@@ -135,11 +135,13 @@ __device__ __forceinline__ void st_keep8(float *p, float4 a, float4 b) {
 __device__ __forceinline__ void ldg8(const void *p, uint4 &a, uint4 &b) {
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
-__device__ __forceinline__ void st_hint2(float2 *p, float2 v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+// one piece of a merge row through the bulk-copy engine (global -> shared): no LSU wavefronts, completion counted in bytes
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void cp_async16_hint(void *smem_dst, const void *gmem_src, uint64_t pol) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "l"(pol) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NPEND>
@@ -162,7 +164,7 @@ __device__ __forceinline__ void unpack8(const uint4 q, float (&f)[8]) {
 }
 
 struct TLayout {
-    unsigned eler_off, x_off, elh_off, hd_off, tot_off, mland_off, si_off, bar_off, total;
+    unsigned eler_off, x_off, elh_off, hd_off, tot_off, mland_off, si_off, dm_off, bar_off, total;
     __host__ __device__ explicit TLayout(int n) {
         eler_off = 0;                                        // [2][n][ESTR] fp32 scores of the current / next star
         x_off = (2u * (unsigned)n * ESTR * 4u + 127u) & ~127u;   // [X_BYTES] B operand
@@ -171,8 +173,9 @@ struct TLayout {
         tot_off = hd_off + 8u * 16u;                         // [52] floats: TotB (16), total dB, pad, fp32 features of the leading member (2 x 16, head parity)
         mland_off = (tot_off + 56u * 4u + 15u) & ~15u;       // [4 warps][2 rows][MROW] floats: records + skip row of the merge rows in flight
         si_off = mland_off + T_WARPS * 2u * MROW * 4u;       // slot handed out for the star after next
-        bar_off = si_off + 16u;                              // MMA mbarrier + tmem slot
-        total = bar_off + 16u;
+        dm_off = si_off + 16u;                               // [8 heads][128 rows] (denominator, max) of the star, written out once per star
+        bar_off = dm_off + 8u * 128u * 8u;                   // MMA mbarrier + tmem slot + 4 merge-row mbarriers
+        total = bar_off + 16u + 4u * 8u;
     }
 };
 
@@ -196,10 +199,13 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
     int *SI = reinterpret_cast<int *>(smem + L.si_off);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.bar_off);
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bar + 1);
+    uint64_t *mbar = bar + 2 + warp;                                   // this warp's merge-row barrier
+    float2 *DMS = reinterpret_cast<float2 *>(smem + L.dm_off);
 
     // ---------------------------------------------------------------- setup
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        for (int w = 0; w < T_WARPS; ++w) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 2 + w)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
     unsigned long long stamp_acc[16] = {};
     long long stamp_last = clock64();
 #endif
-    uint32_t parity = 0;
+    uint32_t parity = 0, mparity = 0;
 
     for (int it = 0; cur < total || cand >= 0 || it == 0; ++it) {
         const int b = cur / n, i = cur - b * n, cbuf = it & 1;
@@ -284,23 +290,23 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         if (nxt < total) issue_scores(nxt / n, nxt % n, cbuf ^ 1);
         // merge rows of MMA shadow `hs` (this warp: rows mlo + 4 hs + warp, + 32): records of both stars and skip row -> shared memory
         auto fetch_merge_rows = [&](int hs) {
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int r = mlo + hs * T_WARPS + warp + 32 * q;
-                if (r >= mhi) break;
-                const size_t node = mnode0 + r;
-                float *dst = MLAND + q * MROW;
-                const float *rv = a.recV + node * 2 * D_;
-                cp_async16_hint(dst + 4 * lane, rv + 4 * lane, pol_stream);
-                cp_async16_hint(dst + D_ + 4 * lane, rv + D_ + 4 * lane, pol_stream);
-                // (all lanes: the cache-policy operand lives in a uniform register, which a divergent lane subset must not
-                // reload; lanes 8..31 repeat the pieces of lanes 0..7)
-                cp_async16_hint(dst + 2 * D_ + 4 * (lane & 7), a.recDM + node * 4 * H_ + 4 * (lane & 7), pol_stream);
-                cp_async16_hint(dst + 2 * D_ + 32 + 4 * lane, a.h + node * D_ + 4 * lane, pol_stream);
+            const int r0 = mlo + hs * T_WARPS + warp;
+            if (lane == 0 && r0 < mhi) {
+                const int rows = (r0 + 32 < mhi) ? 2 : 1;
+                const uint32_t mb = smem_u32(mbar);
+                asm volatile("fence.proxy.async.global;" ::: "memory");    // the records were made visible to the generic proxy
+                mbar_arrive_expect_tx(mb, rows * MROW * 4);
+                for (int q = 0; q < rows; ++q) {
+                    const size_t node = mnode0 + r0 + 32 * q;
+                    const uint32_t dst = smem_u32(MLAND + q * MROW);
+                    bulk_g2s(dst, a.recV + node * 2 * D_, 2 * D_ * 4, mb, pol_stream);
+                    bulk_g2s(dst + 2 * D_ * 4, a.recDM + node * 4 * H_, 4 * H_ * 4, mb, pol_stream);
+                    bulk_g2s(dst + 2 * D_ * 4 + 128, a.h + node * D_, D_ * 4, mb, pol_stream);
+                }
             }
         };
-        if (havemerge) fetch_merge_rows(0);
         cp_async_commit();
+        if (havemerge) fetch_merge_rows(0);
         const float *E = ELER + cbuf * n * ESTR;
         if (havestar) {
             // ---- top-2 of el per head (each warp two heads); the fp16 copy of the CENTRED scores that the branch decision uses
@@ -340,8 +346,10 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         auto merge_rows = [&](int hs) {
             const float4 sc4 = __ldg(reinterpret_cast<const float4 *>(a.bn_scale) + lane), sh4 = __ldg(reinterpret_cast<const float4 *>(a.bn_shift) + lane);
             const float4 bb4 = a.bias ? __ldg(reinterpret_cast<const float4 *>(a.bias) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-            cp_async_wait_group<0>();
-            __syncwarp();
+            if (mlo + hs * T_WARPS + warp < mhi) {                     // (warp-uniform) rows were requested for this shadow
+                mbar_wait(mbar, mparity);
+                mparity ^= 1;
+            }
             KN_STAMP(15);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
@@ -369,7 +377,6 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
             }
             __syncwarp();
             if (hs + 1 < H_) fetch_merge_rows(hs + 1);
-            cp_async_commit();
         };
 
 #pragma unroll 1
@@ -532,12 +539,19 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                     }
                     st_keep8(reinterpret_cast<float *>(rv), v[0], v[1]);
                     st_keep8(reinterpret_cast<float *>(rv + 2), v[2], v[3]);
-                    st_hint2(reinterpret_cast<float2 *>(a.recDM + (my_node * 2 + sl) * 2 * H_ + 2 * head), make_float2(den, M), pol_keep);
+                    DMS[head * 128 + tt] = make_float2(den, M);            // written out with the other heads' at the end of the star
                 }
                 KN_STAMP(12);                                          // partial
             }
         }
         KN_STAMP(12);                                                  // (last) partial
+        if (live) {                                                    // this row's 8 x (denominator, max): one 64-byte chunk of the record
+            const float2 d0 = DMS[tt], d1 = DMS[128 + tt], d2 = DMS[256 + tt], d3 = DMS[384 + tt];
+            const float2 d4 = DMS[512 + tt], d5 = DMS[640 + tt], d6 = DMS[768 + tt], d7 = DMS[896 + tt];
+            float *rd = a.recDM + (my_node * 2 + (i < tt ? 0 : 1)) * 2 * H_;
+            st_keep8(rd, make_float4(d0.x, d0.y, d1.x, d1.y), make_float4(d2.x, d2.y, d3.x, d3.y));
+            st_keep8(rd + 8, make_float4(d4.x, d4.y, d5.x, d5.y), make_float4(d6.x, d6.y, d7.x, d7.y));
+        }
         if (tid == 0) {
             SI[0] = grabbed;
             SI[1] = mtake >= total ? -1 : mtake;                       // (no slices left)
