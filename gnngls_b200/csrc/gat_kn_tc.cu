@@ -86,6 +86,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t &r0, uint32_t &r1) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
 }
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tbase = *tslot;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;            // this warp's lane quarter
-    const int nk = (n + 15) >> 4, nch = (n + 31) >> 5;                 // MMAs (16 members each) / indicator chunks (32 members each)
+    const int nk = (n + 15) >> 4, nch_full = nk >> 1;                  // MMAs (16 members each) / whole indicator chunks (32 members each)
     unsigned char *xrow = Xs + (tt >> 3) * X_KB + (tt & 7) * 16;       // this member's row of the B operand (pieces 128 B apart)
     const int total = B * n;                                           // star slots = merge slices
 
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                     *reinterpret_cast<uint4 *>(xrow + 128) = xa1;
                     *reinterpret_cast<uint4 *>(xrow + 256) = xb0;
                     *reinterpret_cast<uint4 *>(xrow + 384) = xb1;
-                    *reinterpret_cast<uint4 *>(xrow + 512) = xd;       // (columns 40..47 of the operand are never read back: left as they are)
+                    *reinterpret_cast<uint32_t *>(xrow + 512) = xd.x;  // (columns 34..47 of the operand are never read back: left as they are)
                 }
                 if (fix) {                                             // (rare) the leading member of this head: fp32 features for the epilogue
                     if (lead) {
@@ -433,7 +437,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 {
                     const __half2 th2 = __half2half2(th16);
                     const __half *ELH = ELHall + head * KPAD;
-                    for (int c = 0; c < nch; ++c) {
+                    for (int c = 0; c < nch_full; ++c) {
                         uint32_t v[16];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -447,8 +451,21 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                         }
                         tmem_st16(tbase + lane_sel + c * 16, v);
                     }
+                    if (nk & 1) {                                      // an odd number of 16-member MMA steps: half a chunk more
+                        uint32_t v[8];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const uint4 e = *reinterpret_cast<const uint4 *>(ELH + nch_full * 32 + q * 8);
+                            const uint32_t w[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const __half2 r = __hge2(*reinterpret_cast<const __half2 *>(&w[u]), th2);
+                                v[q * 4 + u] = *reinterpret_cast<const uint32_t *>(&r);
+                            }
+                        }
+                        tmem_st8(tbase + lane_sel + nch_full * 16, v);
+                    }
                 }
-                KN_STAMP(4);                                           // operand row + indicator
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // B operand written through the generic proxy
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
