@@ -28,6 +28,20 @@ class GlsArgs(ctypes.Structure):
     ]
 
 
+class LayerParams(ctypes.Structure):
+    """Mirror of struct gnngls_layer_params (include/gnngls_b200.h)."""
+    _fields_ = [('Wfc', _p), ('attn_l', _p), ('attn_r', _p), ('gat_bias', _p), ('bn1_scale', _p), ('bn1_shift', _p),
+                ('W1', _p), ('b1', _p), ('W2', _p), ('b2', _p), ('bn2_scale', _p), ('bn2_shift', _p)]
+
+
+class ModelArgs(ctypes.Structure):
+    """Mirror of struct gnngls_model_args (include/gnngls_b200.h)."""
+    _fields_ = [('B', ctypes.c_int32), ('n', ctypes.c_int32), ('in_dim', ctypes.c_int32), ('out_dim', ctypes.c_int32),
+                ('n_layers', ctypes.c_int32), ('dense_impl', ctypes.c_int32), ('ft_dtype', ctypes.c_int32),
+                ('reserved', ctypes.c_int32), ('x', _p), ('We', _p), ('be', _p), ('Wd', _p), ('bd', _p),
+                ('layers', ctypes.POINTER(LayerParams)), ('y', _p)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/gnngls_b200.h
 SIGNATURES = {
     'gnngls_abi_version': (_i, []),
@@ -49,6 +63,9 @@ SIGNATURES = {
     'gnngls_ff_forward': (_i, [_i, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     'gnngls_decision_forward': (_i, [_p, _i64, _i, _p, _p, _p, _p]),
     'gnngls_regret_postprocess': (_i, [_p, _i64, _d, _d, _p, _p]),
+    'gnngls_sizeof_model_args': (_sz, []),
+    'gnngls_model_forward_workspace_bytes': (_sz, [_i, _i, _i]),
+    'gnngls_model_forward': (_i, [ctypes.POINTER(ModelArgs), _p, _sz, _p]),
 }
 
 # kernels launched per successful C-ABI call (bench.py reports the count as `gpu_launches`)
@@ -60,6 +77,8 @@ KERNELS_PER_CALL = {
     # one fused tcgen05 kernel; the SIMT debug path (impl == 1, first argument) runs two GEMM kernels
     'gnngls_ff_forward': lambda args: 2 if args[0] == 1 else 1,
     'gnngls_decision_forward': 1, 'gnngls_regret_postprocess': 1,
+    # embed + n_layers x (fc, aggregate, feed-forward) + decision
+    'gnngls_model_forward': lambda args: 2 + 3 * args[0].contents.n_layers if hasattr(args[0], 'contents') else 2 + 3 * args[0]._obj.n_layers,
 }
 
 
@@ -124,6 +143,8 @@ def load():
         fn.argtypes = args
     if lib.gnngls_sizeof_gls_args() != ctypes.sizeof(GlsArgs):
         raise RuntimeError('GlsArgs ctypes mirror does not match struct gnngls_gls_args')
+    if lib.gnngls_sizeof_model_args() != ctypes.sizeof(ModelArgs):
+        raise RuntimeError('ModelArgs ctypes mirror does not match struct gnngls_model_args')
     if lib.gnngls_abi_version() != 1:
         raise RuntimeError('libgnngls_b200.so ABI version mismatch')
     _lib = _CountingLib(lib)

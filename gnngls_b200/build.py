@@ -28,6 +28,7 @@ SOURCES = {
     'gat_kn.cu': [],
     'gat_kn_tc.cu': ['-DKN_STAMPS'] if os.environ.get('GNNGLS_KN_STAMPS') else [],   # phase timers (tools/kn_stamps.py)
     'dense.cu': [],
+    'model.cu': [],
 }
 
 

@@ -310,7 +310,44 @@ class EdgePropertyPredictionModel(nn.Module):
         finally:
             _OPERAND_OVERRIDE.pop()
 
+    def _forward_fused(self, G, x, lib, prm, impl, M, dev, in_dim, out_dim):
+        """Whole forward behind one C-ABI call (gnngls_model_forward): K_n line graphs, no per-stage timers."""
+        import ctypes
+        p = _ops._ptr
+        tc = impl == _ops.DENSE_TCGEN05
+        f16 = tc and _op_f16()
+        sfx = '_f16' if f16 else ('_tf32' if tc else '')
+        op_impl = _ops.DENSE_TCGEN05_F16 if f16 else impl
+        if not tc:
+            ft_dtype = _ops.FT_F32
+        elif os.environ.get('GNNGLS_FT_DTYPE', 'f16').lower() == 'tf32' or (_OPERAND_OVERRIDE and _OPERAND_OVERRIDE[-1] == 'tf32'):
+            ft_dtype = _ops.FT_TF32
+        else:
+            ft_dtype = _ops.FT_F16
+        key = ('fused_layers', sfx)
+        if key not in prm:
+            arr = (_lib.LayerParams * len(prm['layers']))()
+            for a, lp in zip(arr, prm['layers']):
+                a.Wfc, a.attn_l, a.attn_r = p(lp['Wfc' + sfx]), p(lp['al']), p(lp['ar'])
+                a.gat_bias = p(lp['gbias'])
+                a.bn1_scale, a.bn1_shift = p(lp['s1']), p(lp['t1'])
+                a.W1, a.b1, a.W2, a.b2 = p(lp['W1' + sfx]), p(lp['b1']), p(lp['W2' + sfx]), p(lp['b2'])
+                a.bn2_scale, a.bn2_shift = p(lp['s2']), p(lp['t2'])
+            prm[key] = arr
+        with torch.cuda.device(dev):
+            nbytes = lib.gnngls_model_forward_workspace_bytes(G.batch_size, G.n, op_impl)
+            wk = _buf(self._ws, 'model_ws', (nbytes,), torch.uint8, dev)
+            y = torch.empty(M, out_dim, dtype=torch.float32, device=dev)
+            args = _lib.ModelArgs(G.batch_size, G.n, in_dim, out_dim, len(prm['layers']), op_impl, ft_dtype, 0, p(x), p(prm['We']),
+                                  p(prm['be']), p(prm['Wd']), p(prm['bd']), prm[key], p(y))
+            _lib.check(lib.gnngls_model_forward(ctypes.byref(args), p(wk), nbytes, _ops._stream()))
+        return y
+
     def _forward_impl(self, G, x, lib, prm, impl, M, dev, in_dim, out_dim):
+        from . import _timing
+        if (G.kind == 'kn' and self.gat_impl in ('auto', 'kn') and G.n <= _KN_MAX_N and _timing._active is None
+                and os.environ.get('GNNGLS_MODEL_FORWARD', 'fused') != 'per_op'):
+            return self._forward_fused(G, x, lib, prm, impl, M, dev, in_dim, out_dim)
         p = _ops._ptr
         with torch.cuda.device(dev):
             tc = impl == _ops.DENSE_TCGEN05

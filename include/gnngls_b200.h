@@ -222,6 +222,41 @@ int gnngls_decision_forward(const float *h, int64_t M, int out_dim, const float 
  * In place allowed. */
 int gnngls_regret_postprocess(const float *y, int64_t M, double scale, double min_, float *regret, void *stream);
 
+/* ---- whole model forward for a batch of line graphs of K_n behind ONE call ---------------------------------------
+ * EdgePropertyPredictionModel.forward (gnngls/models.py:65-70): embed -> n_layers x [GATConv fc, edge-softmax aggregate +
+ * skip + BN1, feed-forward + skip + BN2] -> decision, i.e. the sequence of the entry points above, issued from C on
+ * `stream` with no host round trip in between (26 kernels for the shipped 8-layer model).  Weights are caller-owned
+ * device arrays in the formats the per-op entry points take: for GNNGLS_DENSE_TCGEN05_F16 Wfc/W1/W2 are fp16, for
+ * GNNGLS_DENSE_TCGEN05 fp32 rounded to TF32, for GNNGLS_DENSE_SIMT plain fp32. */
+typedef struct gnngls_layer_params {
+    const void *Wfc;                    /* [128,128]  GATConv.fc.weight                                   */
+    const float *attn_l, *attn_r;       /* [128]      GATConv.attn_l / attn_r, head-major                 */
+    const float *gat_bias;              /* [128] or NULL (DGL >= 0.7 checkpoints)                         */
+    const float *bn1_scale, *bn1_shift; /* [128]      eval-mode BatchNorm1d after the message passing     */
+    const void *W1;                     /* [512,128]                                                      */
+    const float *b1;                    /* [512]                                                          */
+    const void *W2;                     /* [128,512]                                                      */
+    const float *b2;                    /* [128]                                                          */
+    const float *bn2_scale, *bn2_shift; /* [128]                                                          */
+} gnngls_layer_params;
+
+typedef struct gnngls_model_args {
+    int32_t B, n;                       /* batch of line graphs of K_n: M = B*n(n-1)/2 nodes              */
+    int32_t in_dim, out_dim, n_layers;
+    int32_t dense_impl;                 /* gnngls_dense_impl                                              */
+    int32_t ft_dtype;                   /* gnngls_ft_dtype of the projected features                      */
+    int32_t reserved;
+    const float *x;                     /* [M,in_dim]                                                     */
+    const float *We, *be;               /* embed_layer  [128,in_dim], [128]                               */
+    const float *Wd, *bd;               /* decision_layer [out_dim,128], [out_dim]                        */
+    const gnngls_layer_params *layers;  /* HOST array of n_layers entries (device pointers inside)        */
+    float *y;                           /* [M,out_dim]                                                    */
+} gnngls_model_args;
+
+size_t gnngls_sizeof_model_args(void);
+size_t gnngls_model_forward_workspace_bytes(int B, int n, int dense_impl);
+int gnngls_model_forward(const gnngls_model_args *args, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

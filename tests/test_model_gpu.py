@@ -454,3 +454,19 @@ def test_optimality_statistically_unchanged(n, B, mode):
     print(f'TSP{n} x {B} [{mode}]: CPU mean {c_cost.mean():.5f} GPU mean {g_cost.mean():.5f} paired diff {d.mean():+.5f} '
           f'+- {1.96 * se:.5f} (95 %), {100 * rel:.3f} % of the mean; identical tours costs: {(d == 0).mean():.2f}')
     assert abs(d.mean()) <= 3 * se or rel < 1e-3, (n, B, mode, d.mean(), se)
+
+
+def test_fused_model_forward_entry_matches_per_op_path(monkeypatch):
+    """gnngls_model_forward (one C-ABI call for the whole forward) issues the same kernels on the same buffers' contents as
+    the per-op Python loop: bitwise-identical outputs, in the fp16, TF32 and fp32 operand modes."""
+    n, B = 17, 5
+    N = n * (n - 1) // 2
+    x = np.random.default_rng(11).random((B * N, 1)).astype(np.float32)
+    port, m = make_models(gat_bias=True)
+    for dense, mode in (('tcgen05', 'f16'), ('tcgen05', 'tf32'), ('simt', None)):
+        m.operand_dtype = mode
+        monkeypatch.setenv('GNNGLS_MODEL_FORWARD', 'per_op')
+        y_ops = run(m, n, B, x, dense, 'kn')
+        monkeypatch.setenv('GNNGLS_MODEL_FORWARD', 'fused')
+        y_fused = run(m, n, B, x, dense, 'kn')
+        assert np.array_equal(y_ops, y_fused), (dense, mode, np.abs(y_ops - y_fused).max())
