@@ -322,7 +322,7 @@ def main():
         tp = os.path.join(ROOT, 'profiles', 'gat_kn_traffic.json')          # written by tools/ncu_traffic.py from an ncu --set full capture
         if os.path.exists(tp):
             t = json.load(open(tp))
-            if t.get('kernel') == 'gat_kn_tc_kernel' and t.get('n') == n:
+            if str(t.get('kernel', '')).startswith('gat_kn_tc_kernel') and t.get('n') == n:
                 traffic = t['dram_bytes_per_instance_layer'] * per_call_instances
                 traffic_src = t.get('source')
         roof = {'kernel': 'gat_kn_tc_kernel (K_n edge-softmax/aggregate + skip + BN1 on tcgen05)',

@@ -169,13 +169,13 @@ __device__ __forceinline__ void unpack8(const uint4 q, float (&f)[8]) {
 
 struct TLayout {
     unsigned eler_off, x_off, elh_off, hd_off, tot_off, mland_off, si_off, dm_off, bar_off, total;
-    __host__ __device__ explicit TLayout(int n) {
-        eler_off = 0;                                        // [2][n][ESTR] fp32 scores of the current / next star
-        x_off = (2u * (unsigned)n * ESTR * 4u + 127u) & ~127u;   // [X_BYTES] B operand
+    __host__ __device__ TLayout(int n, bool pair) {
+        eler_off = 0;                                        // [2][1 or 2 stars][n][ESTR] fp32 scores of the current / next star(s)
+        x_off = (2u * (pair ? 2u : 1u) * (unsigned)n * ESTR * 4u + 127u) & ~127u;   // [X_BYTES] B operand
         elh_off = x_off + X_BYTES;                           // [8 heads][128] fp16 centred scores el - ref
-        hd_off = elh_off + 8u * 256u;                        // [8][4] words: ref, m1, leading member, "leading member handled in fp32"
-        tot_off = hd_off + 8u * 16u;                         // [52] floats: TotB (16), total dB, pad, fp32 features of the leading member (2 x 16, head parity)
-        mland_off = (tot_off + 56u * 4u + 15u) & ~15u;       // [4 warps][2 rows][MROW] floats: records + skip row of the merge rows in flight
+        hd_off = elh_off + 8u * 256u;                        // [8 heads][1 or 2 stars][4] words: ref, m1, leading member, "leading member handled in fp32"
+        tot_off = hd_off + 16u * 16u;                         // [52] floats: TotB (16), total dB, pad, fp32 features of the leading member (2 x 16, head parity)
+        mland_off = (tot_off + 2u * 56u * 4u + 15u) & ~15u;       // [4 warps][2 rows][MROW] floats: records + skip row of the merge rows in flight
         si_off = mland_off + T_WARPS * 2u * MROW * 4u;       // slot handed out for the star after next
         dm_off = si_off + 16u;                               // [8 heads][128 rows] (denominator, max) of the star, written out once per star
         bar_off = dm_off + 8u * 128u * 8u;                   // MMA mbarrier + tmem slot + 4 merge-row mbarriers
@@ -187,11 +187,16 @@ struct TLayout {
 __device__ __forceinline__ int tri(int i, int n) { return (i * (2 * n - i - 1)) >> 1; }
 __device__ __forceinline__ int kn_local(int i, int k, int n) { return i < k ? tri(i, n) + k - i - 1 : tri(k, n) + i - k - 1; }
 
+// PAIR (n <= 64): two consecutive stars share a CTA iteration -- rows / members 0..63 belong to the first, 64..127 to the second;
+// the indicator is block diagonal (a row's two off-diagonal chunks are zeroed once and never written again), so one MMA chain serves both.
+template <bool PAIR>
 __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a, const int B) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int n = a.n;
-    const TLayout L(n);
+    const TLayout L(n, PAIR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, tt = tid;
+    const int sub = PAIR ? tid >> 6 : 0, lt = PAIR ? tid & 63 : tid;      // which star of the pair; member / row within it
+    constexpr int NS = PAIR ? 2 : 1;
     const size_t N = (size_t)n * (n - 1) / 2;
 
     float *ELER = reinterpret_cast<float *>(smem + L.eler_off);
@@ -221,17 +226,29 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tbase = *tslot;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;            // this warp's lane quarter
-    const int nk = (n + 15) >> 4, nch_full = nk >> 1;                  // MMAs (16 members each) / whole indicator chunks (32 members each)
+    const int nk = PAIR ? KPAD / 16 : (n + 15) >> 4, nch_full = nk >> 1;   // MMAs (16 members each) / whole indicator chunks (32 members each)
     unsigned char *xrow = Xs + (tt >> 3) * X_KB + (tt & 7) * 16;       // this member's row of the B operand (pieces 128 B apart)
-    const int total = B * n;                                           // star slots = merge slices
+    const int total = B * n;                                           // stars = merge slices
+    const int slots = PAIR ? (total + 1) >> 1 : total;                 // CTA iterations with a star (pair)
+    if (PAIR) {                                                        // the off-diagonal indicator blocks: zero, once
+        const uint32_t z[16] = {};
+        for (int c = 0; c < 4; ++c) tmem_st16(tbase + lane_sel + c * 16, z);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
 
     // scores of star (sb, si) -> buffer `buf` (cp.async; the vertex's own slot is zero-filled)
-    auto issue_scores = [&](int sb, int si, int buf) {
-        for (int idx = tid; idx < 4 * n; idx += T_THREADS) {
-            const int k = idx >> 2, p = idx & 3;
-            float *dst = ELER + (buf * n + k) * ESTR + p * 4;
-            if (k != si) cp_async16(dst, (p < 2 ? a.el : a.er) + ((size_t)sb * N + kn_local(si, k, n)) * H_ + (p & 1) * 4);
-            else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto issue_scores = [&](int slot, int buf) {
+#pragma unroll
+        for (int sp = 0; sp < NS; ++sp) {
+            const int st = NS * slot + sp;
+            if (st >= total) break;
+            const int sb = st / n, si = st - sb * n;
+            for (int idx = tid; idx < 4 * n; idx += T_THREADS) {
+                const int k = idx >> 2, p = idx & 3;
+                float *dst = ELER + ((buf * NS + sp) * n + k) * ESTR + p * 4;
+                if (k != si) cp_async16(dst, (p < 2 ? a.el : a.er) + ((size_t)sb * N + kn_local(si, k, n)) * H_ + (p & 1) * 4);
+                else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
     };
 
@@ -245,7 +262,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
     int cur = SI[0], nxt = SI[1];                                      // star slots are handed out in order, one star ahead
     int cand = -1;                                                     // merge slice taken by this CTA, not merged yet (-1: none)
     __syncthreads();
-    if (cur < total) issue_scores(cur / n, cur % n, 0);
+    if (cur < slots) issue_scores(cur, 0);
     cp_async_commit();
 #ifdef KN_STAMPS
     unsigned long long stamp_acc[16] = {};
@@ -253,9 +270,12 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
 #endif
     uint32_t parity = 0, mparity = 0;
 
-    for (int it = 0; cur < total || cand >= 0 || it == 0; ++it) {
-        const int b = cur / n, i = cur - b * n, cbuf = it & 1;
-        const bool havestar = cur < total;
+    for (int it = 0; cur < slots || cand >= 0 || it == 0; ++it) {
+        const int cbuf = it & 1;
+        const bool havestar = cur < slots;                             // (the CTA has a star, or a pair, in this iteration)
+        const int star = NS * cur + sub;                               // this thread's star
+        const bool mystar = havestar && star < total;
+        const int b = mystar ? star / n : 0, i = mystar ? star - b * n : 0;
         int grabbed = 0;
         if (tid == 0) {
             grabbed = atomicAdd(ctr, 1);                               // the slot after next (needed at the end of the iteration)
@@ -269,8 +289,8 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
             SI[2] = rdy;
         }
         // this thread as member / destination row tt of the current star; its features for the first head
-        const bool live = havestar && tt < n && tt != i;
-        const int my_local = live ? kn_local(i, tt, n) : 0;
+        const bool live = mystar && lt < n && lt != i;
+        const int my_local = live ? kn_local(i, lt, n) : 0;
         const size_t my_node = (size_t)b * N + my_local;
         const uint4 *ftrow = reinterpret_cast<const uint4 *>(static_cast<const unsigned char *>(a.ft) + my_node * 256);
         uint4 f0 = make_uint4(0u, 0u, 0u, 0u), f1 = f0;
@@ -291,7 +311,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
             for (int idx = tid; idx < (mhi - mlo) * 4; idx += T_THREADS)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h + (mnode0 + mlo) * D_ + 32 * idx));
         }
-        if (nxt < total) issue_scores(nxt / n, nxt % n, cbuf ^ 1);
+        if (nxt < slots) issue_scores(nxt, cbuf ^ 1);
         // merge rows of MMA shadow `hs` (this warp: rows mlo + 4 hs + warp, + 32): records of both stars and skip row -> shared memory
         auto fetch_merge_rows = [&](int hs) {
             const int r0 = mlo + hs * T_WARPS + warp;
@@ -311,19 +331,23 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         };
         cp_async_commit();
         if (havemerge) fetch_merge_rows(0);
-        const float *E = ELER + cbuf * n * ESTR;
+        const float *E = ELER + (cbuf * NS + sub) * n * ESTR;          // this thread's star
         if (havestar) {
-            // ---- top-2 of el per head (each warp two heads); the fp16 copy of the CENTRED scores that the branch decision uses
+            // ---- top-2 of el per (head, star): each warp takes 8 NS / 4 of them; the fp16 copy of the CENTRED scores that the branch
+            // decision uses, at member position 64 sp + k
 #pragma unroll
-            for (int hq = 0; hq < H_ / T_WARPS; ++hq) {
-                const int head = warp * (H_ / T_WARPS) + hq;
-                float ev[KPAD / 32];
+            for (int hq = 0; hq < H_ * NS / T_WARPS; ++hq) {
+                const int combo = warp * (H_ * NS / T_WARPS) + hq, head = combo % H_, sp = combo / H_;
+                const int st = NS * cur + sp, ip = st < total ? st % n : -1;    // (ip < 0: no such star -- an odd star count)
+                const float *Ep = ELER + (cbuf * NS + sp) * n * ESTR;
+                constexpr int NQ = PAIR ? 2 : KPAD / 32;
+                float ev[NQ];
                 Top2 t2{-INFINITY, -INFINITY, 0};
 #pragma unroll
-                for (int q = 0; q < KPAD / 32; ++q) {
+                for (int q = 0; q < NQ; ++q) {
                     const int k = lane + 32 * q;
-                    const bool ok = k < n && k != i;
-                    ev[q] = ok ? E[k * ESTR + head] : -INFINITY;
+                    const bool ok = ip >= 0 && k < n && k != ip;
+                    ev[q] = ok ? Ep[k * ESTR + head] : -INFINITY;
                     if (ok) t2 = top2_merge(t2, Top2{ev[q], -INFINITY, k});
                 }
 #pragma unroll
@@ -334,11 +358,12 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                     o.a1 = __shfl_xor_sync(0xffffffffu, t2.a1, off);
                     t2 = top2_merge(t2, o);
                 }
-                const bool fix = t2.m1 - t2.m2 > kLeadGap;             // (n >= 3: the runner-up exists)
-                const float ref = fix ? t2.m2 : t2.m1;
+                const bool fix = ip >= 0 && t2.m1 - t2.m2 > kLeadGap;  // (n >= 3: the runner-up exists)
+                const float ref = ip < 0 ? 0.f : (fix ? t2.m2 : t2.m1);
 #pragma unroll
-                for (int q = 0; q < KPAD / 32; ++q) ELHall[head * KPAD + lane + 32 * q] = __float2half_rn(ev[q] - ref);
-                if (lane == 0) *reinterpret_cast<float4 *>(HD + head * 4) = make_float4(ref, t2.m1, __int_as_float(t2.a1), __int_as_float(fix ? 1 : 0));
+                for (int q = 0; q < NQ; ++q) ELHall[head * KPAD + (PAIR ? 64 * sp : 0) + lane + 32 * q] = __float2half_rn(ev[q] - ref);
+                if (lane == 0)
+                    *reinterpret_cast<float4 *>(HD + (head * NS + sp) * 4) = make_float4(ref, t2.m1, __int_as_float(t2.a1), __int_as_float(fix ? 1 : 0));
             }
             KN_STAMP(2);                                               // slice setup, top-2
             __syncthreads();
@@ -386,18 +411,19 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
 #pragma unroll 1
         for (int head = 0; head < H_; ++head) {
             if (havestar) {
-                const float4 hd = *reinterpret_cast<const float4 *>(HD + head * 4);   // ref, m1, leading member, "leading member in fp32"
+                const float4 hd = *reinterpret_cast<const float4 *>(HD + (head * NS + sub) * 4);   // ref, m1, leading member, "leading member in fp32"
                 const float ref = hd.x;
-                const bool fix = __float_as_int(hd.w) != 0;            // CTA-uniform
-                const bool lead = fix && tt == __float_as_int(hd.z);
-                const float erh = live ? E[tt * ESTR + 8 + head] : 0.f;
-                const __half th16 = live ? __float2half_rn(-erh - ref) : __float2half_rn(tt == i ? -INFINITY : INFINITY);
-                float *TOTl = TOT + 20 + (head & 1) * 16;              // fp32 features of the leading member (parity buffer)
+                const bool fix = __float_as_int(hd.w) != 0;            // uniform over the star's threads (whole warps)
+                const bool lead = fix && lt == __float_as_int(hd.z);
+                const float erh = live ? E[lt * ESTR + 8 + head] : 0.f;
+                const __half th16 = live ? __float2half_rn(-erh - ref) : __float2half_rn((mystar && lt == i) ? -INFINITY : INFINITY);
+                float *TOTs = TOT + sub * 56;                          // this star's column totals / leading-member features
+                float *TOTl = TOTs + 20 + (head & 1) * 16;             // fp32 features of the leading member (parity buffer)
                 // ---- B operand row of member tt: [A ft | A' ft | A A' 0...]
                 if (tt < 16 * nk) {
                     uint4 xa0 = make_uint4(0u, 0u, 0u, 0u), xa1 = xa0, xb0 = xa0, xb1 = xa0, xd = xa0;
                     if (live && !lead) {
-                        const float d = E[tt * ESTR + head] - ref;
+                        const float d = E[lt * ESTR + head] - ref;
                         const __half A16 = __float2half_rn(ex2(d)), A516 = __float2half_rn(ex2(kSlope * d));
                         const __half2 hA = __half2half2(A16), hB = __half2half2(A516);
                         auto mul4 = [](uint4 f, __half2 s) {
@@ -437,7 +463,8 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 {
                     const __half2 th2 = __half2half2(th16);
                     const __half *ELH = ELHall + head * KPAD;
-                    for (int c = 0; c < nch_full; ++c) {
+                    const int c_lo = PAIR ? 2 * sub : 0, c_hi = PAIR ? 2 * sub + 2 : nch_full;   // (PAIR: own star's chunks only)
+                    for (int c = c_lo; c < c_hi; ++c) {
                         uint32_t v[16];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -451,7 +478,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                         }
                         tmem_st16(tbase + lane_sel + c * 16, v);
                     }
-                    if (nk & 1) {                                      // an odd number of 16-member MMA steps: half a chunk more
+                    if (!PAIR && (nk & 1)) {                           // an odd number of 16-member MMA steps: half a chunk more
                         uint32_t v[8];
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
@@ -495,22 +522,23 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 tmem_ld2(tbase + lane_sel + 96, SD0, SD1);             // sum A, sum A' over the A-branch members
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                if (tt == i) {                                         // the all-ones row: column totals
+                float *TOTs = TOT + sub * 56;
+                if (mystar && lt == i) {                               // the all-ones row of this star: column totals
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<uint4 *>(TOT + 4 * q) = make_uint4(SB[4 * q], SB[4 * q + 1], SB[4 * q + 2], SB[4 * q + 3]);
-                    TOT[16] = __uint_as_float(SD1);
+                        *reinterpret_cast<uint4 *>(TOTs + 4 * q) = make_uint4(SB[4 * q], SB[4 * q + 1], SB[4 * q + 2], SB[4 * q + 3]);
+                    TOTs[16] = __uint_as_float(SD1);
                 }
                 KN_STAMP(10);                                          // accumulators -> registers
                 __syncthreads();                                       // totals visible; every row has its accumulators
                 KN_STAMP(11);                                          // barrier B
                 if (live) {
                     // ---- this star's partial for destination tt (fp32): v = C1 SA + C2 (Tot - SB) - self (+ leading member)
-                    const float4 hd = *reinterpret_cast<const float4 *>(HD + head * 4);
+                    const float4 hd = *reinterpret_cast<const float4 *>(HD + (head * NS + sub) * 4);
                     const float ref = hd.x;
                     const bool fix = __float_as_int(hd.w) != 0;
-                    const bool lead = fix && tt == __float_as_int(hd.z);
-                    const float erh = E[tt * ESTR + 8 + head];
+                    const bool lead = fix && lt == __float_as_int(hd.z);
+                    const float erh = E[lt * ESTR + 8 + head];
                     const __half th16 = __float2half_rn(-erh - ref);
                     const float s = ref + erh;
                     const float c = ex2(-0.8f * fabsf(s));
@@ -519,7 +547,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                     const bool self_a = __hge(ELHall[head * KPAD + tt], th16);     // the branch the MMA put this row's own member in
                     const uint32_t xdw = *reinterpret_cast<const uint32_t *>(xrow + 512);
                     const float2 aa = __half22float2(*reinterpret_cast<const __half2 *>(&xdw));   // (A, A') as the MMA saw them
-                    float den = fmaf(C1, __uint_as_float(SD0), C2 * (TOT[16] - __uint_as_float(SD1))) - (self_a ? C1 * aa.x : C2 * aa.y);
+                    float den = fmaf(C1, __uint_as_float(SD0), C2 * (TOTs[16] - __uint_as_float(SD1))) - (self_a ? C1 * aa.x : C2 * aa.y);
                     float scl = 1.f;
                     const bool addlead = fix && !lead;
                     if (addlead) {                                     // the leading member joins in fp32 with weight exactly 1
@@ -530,13 +558,13 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                     }
                     const float k1 = C1 * scl, k2 = C2 * scl, ks = (self_a ? C1 : C2) * scl;
                     const unsigned char *xself = xrow + (self_a ? 0 : 256);        // this member's own products in the branch it was counted in
-                    const int sl = i < tt ? 0 : 1;                     // slot 0: written by the star of the lower vertex
+                    const int sl = i < lt ? 0 : 1;                     // slot 0: written by the star of the lower vertex
                     float4 *rv = reinterpret_cast<float4 *>(a.recV + (my_node * 2 + sl) * D_ + head * F_);
-                    const float *TOTl = TOT + 20 + (head & 1) * 16;
+                    const float *TOTl = TOTs + 20 + (head & 1) * 16;
                     float4 v[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {                      // 4 features at a time
-                        const float4 t4 = *reinterpret_cast<const float4 *>(TOT + 4 * q);
+                        const float4 t4 = *reinterpret_cast<const float4 *>(TOTs + 4 * q);
                         const uint2 xs = *reinterpret_cast<const uint2 *>(xself + (q >> 1) * 128 + (q & 1) * 8);
                         const float2 x01 = __half22float2(*reinterpret_cast<const __half2 *>(&xs.x)), x23 = __half22float2(*reinterpret_cast<const __half2 *>(&xs.y));
                         v[q].x = fmaf(k1, __uint_as_float(SA[4 * q]), fmaf(-k2, __uint_as_float(SB[4 * q]), fmaf(-ks, x01.x, k2 * t4.x)));
@@ -565,7 +593,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         if (live) {                                                    // this row's 8 x (denominator, max): one 64-byte chunk of the record
             const float2 d0 = DMS[tt], d1 = DMS[128 + tt], d2 = DMS[256 + tt], d3 = DMS[384 + tt];
             const float2 d4 = DMS[512 + tt], d5 = DMS[640 + tt], d6 = DMS[768 + tt], d7 = DMS[896 + tt];
-            float *rd = a.recDM + (my_node * 2 + (i < tt ? 0 : 1)) * 2 * H_;
+            float *rd = a.recDM + (my_node * 2 + (i < lt ? 0 : 1)) * 2 * H_;
             st_keep8(rd, make_float4(d0.x, d0.y, d1.x, d1.y), make_float4(d2.x, d2.y, d3.x, d3.y));
             st_keep8(rd + 8, make_float4(d4.x, d4.y, d5.x, d5.y), make_float4(d6.x, d6.y, d7.x, d7.y));
         }
@@ -577,6 +605,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         if (havestar && tid == 0) {
             __threadfence();
             atomicAdd(a.flags + b, 1);                                 // one more star of instance b is out
+            if (PAIR && NS * cur + 1 < total) atomicAdd(a.flags + (NS * cur + 1) / n, 1);   // ... and the second of the pair
         }
         cur = nxt;
         nxt = SI[0];
@@ -605,20 +634,23 @@ size_t kn_tc_workspace_bytes(int B, int n) {
 int launch_kn_tc(const KnArgs &args_in, int B, void *workspace, cudaStream_t st) {
     KnArgs args = args_in;
     const int n = args.n;
-    const TLayout L(n);
+    const bool pair = n <= 64;                                         // two stars per CTA iteration
+    const TLayout L(n, pair);
     GNNGLS_REQUIRE(n <= KPAD, GNNGLS_ERR_UNSUPPORTED, "the tcgen05 K_n kernel handles n <= %d", KPAD);
     const size_t M = (size_t)B * ((size_t)n * (n - 1) / 2);
     args.recV = static_cast<float *>(workspace);
     args.recDM = args.recV + M * 2 * D_;
     args.flags = reinterpret_cast<int *>(args.recDM + M * 4 * H_);
     GNNGLS_CUDA_OK(cudaMemsetAsync(args.flags, 0, sizeof(int) * ((size_t)B + 4), st));
-    GNNGLS_CUDA_OK(cudaFuncSetAttribute(gat_kn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    GNNGLS_CUDA_OK(cudaFuncSetAttribute(gat_kn_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    auto kernel = pair ? gat_kn_tc_kernel<true> : gat_kn_tc_kernel<false>;
+    GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int64_t stars = (int64_t)B * n;
     GNNGLS_REQUIRE(stars < ((int64_t)1 << 30), GNNGLS_ERR_UNSUPPORTED, "B*n too large for one launch");
     const int grid_max = gnngls::device_sm_count() * 4;
-    const unsigned grid = (unsigned)(stars < grid_max ? stars : grid_max);
-    gat_kn_tc_kernel<<<grid, T_THREADS, L.total, st>>>(args, B);
+    const int64_t slots = pair ? (stars + 1) / 2 : stars;
+    const unsigned grid = (unsigned)(slots < grid_max ? slots : grid_max);
+    kernel<<<grid, T_THREADS, L.total, st>>>(args, B);
     GNNGLS_LAUNCH_OK("gat_kn_tc_kernel");
     return GNNGLS_OK;
 }
