@@ -269,6 +269,9 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
     long long stamp_last = clock64();
 #endif
     uint32_t parity = 0, mparity = 0;
+    // BN1 scale / shift and the GAT bias of this lane's four features (merge rows: one warp per row)
+    const float4 sc4 = __ldg(reinterpret_cast<const float4 *>(a.bn_scale) + lane), sh4 = __ldg(reinterpret_cast<const float4 *>(a.bn_shift) + lane);
+    const float4 bb4 = a.bias ? __ldg(reinterpret_cast<const float4 *>(a.bias) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int it = 0; cur < slots || cand >= 0 || it == 0; ++it) {
         const int cbuf = it & 1;
@@ -373,8 +376,6 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         // the merge rows fetched one shadow ago: combine the two stars' records in fixed (lower, higher) order, apply bias + skip +
         // BN1, write h1; then fetch the rows of the next shadow
         auto merge_rows = [&](int hs) {
-            const float4 sc4 = __ldg(reinterpret_cast<const float4 *>(a.bn_scale) + lane), sh4 = __ldg(reinterpret_cast<const float4 *>(a.bn_shift) + lane);
-            const float4 bb4 = a.bias ? __ldg(reinterpret_cast<const float4 *>(a.bias) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (mlo + hs * T_WARPS + warp < mhi) {                     // (warp-uniform) rows were requested for this shadow
                 mbar_wait(mbar, mparity);
                 mparity ^= 1;
@@ -410,13 +411,14 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
 
 #pragma unroll 1
         for (int head = 0; head < H_; ++head) {
+            // (per head and star: ref, m1, leading member, "leading member in fp32"; meaningless without a star)
+            const float4 hd = havestar ? *reinterpret_cast<const float4 *>(HD + (head * NS + sub) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float ref = hd.x;
+            const bool fix = __float_as_int(hd.w) != 0;                // uniform over the star's threads (whole warps)
+            const bool lead = fix && lt == __float_as_int(hd.z);
+            const float erh = live ? E[lt * ESTR + 8 + head] : 0.f;
+            const __half th16 = live ? __float2half_rn(-erh - ref) : __float2half_rn((mystar && lt == i) ? -INFINITY : INFINITY);
             if (havestar) {
-                const float4 hd = *reinterpret_cast<const float4 *>(HD + (head * NS + sub) * 4);   // ref, m1, leading member, "leading member in fp32"
-                const float ref = hd.x;
-                const bool fix = __float_as_int(hd.w) != 0;            // uniform over the star's threads (whole warps)
-                const bool lead = fix && lt == __float_as_int(hd.z);
-                const float erh = live ? E[lt * ESTR + 8 + head] : 0.f;
-                const __half th16 = live ? __float2half_rn(-erh - ref) : __float2half_rn((mystar && lt == i) ? -INFINITY : INFINITY);
                 float *TOTs = TOT + sub * 56;                          // this star's column totals / leading-member features
                 float *TOTl = TOTs + 20 + (head & 1) * 16;             // fp32 features of the leading member (parity buffer)
                 // ---- B operand row of member tt: [A ft | A' ft | A A' 0...]
@@ -534,12 +536,6 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 KN_STAMP(11);                                          // barrier B
                 if (live) {
                     // ---- this star's partial for destination tt (fp32): v = C1 SA + C2 (Tot - SB) - self (+ leading member)
-                    const float4 hd = *reinterpret_cast<const float4 *>(HD + (head * NS + sub) * 4);
-                    const float ref = hd.x;
-                    const bool fix = __float_as_int(hd.w) != 0;
-                    const bool lead = fix && lt == __float_as_int(hd.z);
-                    const float erh = E[lt * ESTR + 8 + head];
-                    const __half th16 = __float2half_rn(-erh - ref);
                     const float s = ref + erh;
                     const float c = ex2(-0.8f * fabsf(s));
                     const float C1 = s >= 0.f ? 1.f : c, C2 = s >= 0.f ? c : 1.f;
@@ -561,12 +557,14 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                     const int sl = i < lt ? 0 : 1;                     // slot 0: written by the star of the lower vertex
                     float4 *rv = reinterpret_cast<float4 *>(a.recV + (my_node * 2 + sl) * D_ + head * F_);
                     const float *TOTl = TOTs + 20 + (head & 1) * 16;
+                    const uint4 xq0 = *reinterpret_cast<const uint4 *>(xself), xq1 = *reinterpret_cast<const uint4 *>(xself + 128);
+                    const uint32_t xsw[8] = {xq0.x, xq0.y, xq0.z, xq0.w, xq1.x, xq1.y, xq1.z, xq1.w};
                     float4 v[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {                      // 4 features at a time
                         const float4 t4 = *reinterpret_cast<const float4 *>(TOTs + 4 * q);
-                        const uint2 xs = *reinterpret_cast<const uint2 *>(xself + (q >> 1) * 128 + (q & 1) * 8);
-                        const float2 x01 = __half22float2(*reinterpret_cast<const __half2 *>(&xs.x)), x23 = __half22float2(*reinterpret_cast<const __half2 *>(&xs.y));
+                        const uint32_t xs0 = xsw[2 * q], xs1 = xsw[2 * q + 1];
+                        const float2 x01 = __half22float2(*reinterpret_cast<const __half2 *>(&xs0)), x23 = __half22float2(*reinterpret_cast<const __half2 *>(&xs1));
                         v[q].x = fmaf(k1, __uint_as_float(SA[4 * q]), fmaf(-k2, __uint_as_float(SB[4 * q]), fmaf(-ks, x01.x, k2 * t4.x)));
                         v[q].y = fmaf(k1, __uint_as_float(SA[4 * q + 1]), fmaf(-k2, __uint_as_float(SB[4 * q + 1]), fmaf(-ks, x01.y, k2 * t4.y)));
                         v[q].z = fmaf(k1, __uint_as_float(SA[4 * q + 2]), fmaf(-k2, __uint_as_float(SB[4 * q + 2]), fmaf(-ks, x23.x, k2 * t4.z)));
