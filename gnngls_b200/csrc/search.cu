@@ -12,7 +12,10 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <cooperative_groups.h>
 #include "common.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -83,6 +86,46 @@ __device__ Best block_reduce_best(Best v, bool fi, Best *red) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// who shares one all-pairs sweep: the warps of one CTA (Solo), or the warps of every CTA of a thread-block
+// cluster (Cluster; SURVEY.md section 8(f) rank 3, north star (4) "one CTA or cluster per instance").  Rows i of the
+// scan are dealt round-robin to the team's warps; the winners are combined with pick(), a total order on
+// (delta, scan rank), so the result does not depend on how the rows were dealt -- it is the reference's
+// sequential first-strict-minimum whatever the team.
+// ----------------------------------------------------------------------------------------------
+constexpr int kMaxCluster = 16;
+
+struct Solo {
+    __device__ __forceinline__ int first_row(int warp) const { return warp; }
+    __device__ __forceinline__ int row_stride(int nw) const { return nw; }
+    __device__ __forceinline__ Best reduce(Best v, bool fi, Best *red) { return block_reduce_best(v, fi, red); }
+    __device__ __forceinline__ bool lead() const { return true; }
+};
+
+// Every CTA of the cluster holds a replica of the tour; each sweeps its share of the rows, writes its winner into
+// slot [rank] of EVERY member's exchange buffer through distributed shared memory, and after one cluster barrier all
+// members hold the same kMaxCluster candidates and apply the same move to their replica.  The buffer is double
+// buffered by the parity of the sweep count: a member can only be one barrier ahead, so the slots it overwrites were
+// read two barriers ago.
+struct Cluster {
+    int rank, size, parity;
+    Best *xch;   // [2][kMaxCluster] in this CTA's shared memory
+    __device__ __forceinline__ int first_row(int warp) const { return warp * size + rank; }
+    __device__ __forceinline__ int row_stride(int nw) const { return nw * size; }
+    __device__ __forceinline__ bool lead() const { return rank == 0; }   // the member that owns the global results
+    __device__ Best reduce(Best v, bool fi, Best *red) {
+        v = block_reduce_best(v, fi, red);
+        cg::cluster_group cl = cg::this_cluster();
+        Best *mine = xch + parity * kMaxCluster;
+        if ((int)threadIdx.x < size) *cl.map_shared_rank(mine + rank, threadIdx.x) = v;
+        cl.sync();
+        Best w = mine[0];
+        for (int q = 1; q < size; ++q) w = pick(w, mine[q], fi);
+        parity ^= 1;
+        return w;
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
 // distance-matrix accessors
 // ----------------------------------------------------------------------------------------------
 struct MatPlain {
@@ -108,14 +151,14 @@ struct MatPen {
 // ----------------------------------------------------------------------------------------------
 // two_opt_cost (operators.py:14-29), i<j: ((D[a,c] + D[b,d]) - D[a,b]) - D[c,d]
 //   a=t[i] b=t[i-1] c=t[j] d=t[j-1];  E[p] := D[t[p], t[p-1]] so D[a,b]=E[i], D[c,d]=E[j]
-template <class M>
-__device__ Best sweep_two_opt_a2a(const int *t, int n, const M &D, double *E, bool fi, Best *red) {
+template <class M, class T>
+__device__ Best sweep_two_opt_a2a(const int *t, int n, const M &D, double *E, bool fi, Best *red, T &team) {
     for (int p = 1 + threadIdx.x; p <= n - 1; p += blockDim.x) E[p] = D(t[p], t[p - 1]);
     __syncthreads();
     Best best;
     best.delta = 0.0; best.key = -1; best.pad = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int i = 1 + warp; i <= n - 3; i += nw) {
+    for (int i = 1 + team.first_row(warp); i <= n - 3; i += team.row_stride(nw)) {
         const int a = t[i], b = t[i - 1];
         const double Ei = E[i];
         for (int j = i + 2 + lane; j <= n - 1; j += 32) {
@@ -126,20 +169,20 @@ __device__ Best sweep_two_opt_a2a(const int *t, int n, const M &D, double *E, bo
             consider(best, x, (i << 16) | j, fi);
         }
     }
-    return block_reduce_best(best, fi, red);
+    return team.reduce(best, fi, red);
 }
 
 // relocate_cost (operators.py:83-103): (((((-D[a,b]) - D[b,c]) + D[a,c]) - D[d,e]) + D[d,b]) + D[b,e]
 //   a=t[i-1] b=t[i] c=t[i+1]; (d,e) = (t[q],t[q+1]) with q = j if i<j else j-1
 //   E[p] := D[t[p], t[p+1]] so D[a,b]=E[i-1], D[b,c]=E[i], D[d,e]=E[q]
-template <class M>
-__device__ Best sweep_relocate_a2a(const int *t, int n, const M &D, double *E, bool fi, Best *red) {
+template <class M, class T>
+__device__ Best sweep_relocate_a2a(const int *t, int n, const M &D, double *E, bool fi, Best *red, T &team) {
     for (int p = threadIdx.x; p <= n - 1; p += blockDim.x) E[p] = D(t[p], t[p + 1]);
     __syncthreads();
     Best best;
     best.delta = 0.0; best.key = -1; best.pad = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int i = 1 + warp; i <= n - 1; i += nw) {
+    for (int i = 1 + team.first_row(warp); i <= n - 1; i += team.row_stride(nw)) {
         const int a = t[i - 1], b = t[i], c = t[i + 1];
         double base = __dsub_rn(-E[i - 1], E[i]);
         base = __dadd_rn(base, D(a, c));
@@ -153,7 +196,7 @@ __device__ Best sweep_relocate_a2a(const int *t, int n, const M &D, double *E, b
             consider(best, x, (i << 16) | j, fi);
         }
     }
-    return block_reduce_best(best, fi, red);
+    return team.reduce(best, fi, red);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -250,6 +293,7 @@ struct Smem {
     double *E;       // n+1 per-position edge terms
     double *slot;    // 4 doubles of block-shared scalars
     Best *red;       // 33
+    Best *xch;       // 2 x kMaxCluster winners exchanged between the CTAs of a cluster
     int *tour;       // n+1
     int *tmp;        // n+1
     int *best_tour;  // n+1 (GLS only)
@@ -266,6 +310,7 @@ __host__ __device__ inline size_t smem_layout(int n, bool stage_d, bool gls, boo
     size_t oE = take(sizeof(double) * (n + 1));
     size_t oS = take(sizeof(double) * 4);
     size_t oR = take(sizeof(Best) * 33);
+    size_t oX = take(sizeof(Best) * 2 * kMaxCluster);
     size_t oT = take(sizeof(int) * (n + 1));
     size_t oM = take(sizeof(int) * (n + 1));
     size_t oB = gls ? take(sizeof(int) * (n + 1)) : 0;
@@ -276,6 +321,7 @@ __host__ __device__ inline size_t smem_layout(int n, bool stage_d, bool gls, boo
         s->E = reinterpret_cast<double *>(base + oE);
         s->slot = reinterpret_cast<double *>(base + oS);
         s->red = reinterpret_cast<Best *>(base + oR);
+        s->xch = reinterpret_cast<Best *>(base + oX);
         s->tour = reinterpret_cast<int *>(base + oT);
         s->tmp = reinterpret_cast<int *>(base + oM);
         s->best_tour = gls ? reinterpret_cast<int *>(base + oB) : nullptr;
@@ -305,16 +351,16 @@ struct EventLog {
 
 // algorithms.py:111-132.  All threads call; tour in shared memory is updated in place; *cost is
 // a block-shared slot updated by thread 0.  Returns nothing; counters are thread-0 registers.
-template <class M>
+template <class M, class T>
 __device__ void local_search_dev(const Smem &s, int n, const M &D, bool fi, double *cost_slot,
-                                 EventLog &log, long long *cnt /* thread-0 local [4] */) {
+                                 EventLog &log, long long *cnt /* thread-0 local [4] */, T &team) {
     bool improved = true;
     while (improved) {
         improved = false;
 #pragma unroll 1
         for (int op = 0; op < 2; ++op) {
-            Best b = (op == 0) ? sweep_two_opt_a2a(s.tour, n, D, s.E, fi, s.red)
-                               : sweep_relocate_a2a(s.tour, n, D, s.E, fi, s.red);
+            Best b = (op == 0) ? sweep_two_opt_a2a(s.tour, n, D, s.E, fi, s.red, team)
+                               : sweep_relocate_a2a(s.tour, n, D, s.E, fi, s.red, team);
             if (threadIdx.x == 0) cnt[op] += 1;
             if (b.key >= 0) {                                  // delta < 0 by construction
                 improved = true;
@@ -333,19 +379,45 @@ __device__ void local_search_dev(const Smem &s, int n, const M &D, bool fi, doub
 // ----------------------------------------------------------------------------------------------
 // kernels
 // ----------------------------------------------------------------------------------------------
-template <bool STAGE_D>
+// Team of the launch: CL == false -> the CTA; CL == true -> the cluster the CTA belongs to (instances are then dealt
+// to clusters, every member keeps a tour replica and member 0 writes the results).
+template <bool CL> struct TeamOf { using type = Solo; };
+template <> struct TeamOf<true> { using type = Cluster; };
+
+template <bool CL>
+__device__ __forceinline__ typename TeamOf<CL>::type make_team(const Smem &s, int *inst0, int *inst_stride) {
+    typename TeamOf<CL>::type team;
+    if constexpr (CL) {
+        cg::cluster_group cl = cg::this_cluster();
+        team.rank = (int)cl.block_rank();
+        team.size = (int)cl.num_blocks();
+        team.parity = 0;
+        team.xch = s.xch;
+        *inst0 = (int)blockIdx.x / team.size;
+        *inst_stride = (int)gridDim.x / team.size;
+    } else {
+        *inst0 = (int)blockIdx.x;
+        *inst_stride = (int)gridDim.x;
+    }
+    return team;
+}
+
+template <bool STAGE_D, bool CL>
 __global__ void moves_kernel(int op, bool o2a, const double *Dg, int64_t d_stride, const int *tours,
                              const int *pos, int B, int n, int fi, double *out_delta, int *out_move,
                              int *out_tours) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem s;
     smem_layout(n, STAGE_D, false, false, &s, smem_raw);
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    int inst0, inst_stride;
+    auto team = make_team<CL>(s, &inst0, &inst_stride);
+    const bool writer = team.lead();
+    for (int b = inst0; b < B; b += inst_stride) {
         const double *Db = Dg + (size_t)b * d_stride;
         for (int p = threadIdx.x; p <= n; p += blockDim.x) s.tour[p] = tours[(size_t)b * (n + 1) + p];
         MatPlain D;
         if (STAGE_D) {
-            if (b == blockIdx.x || d_stride != 0) stage_matrix(s.D, Db, n);
+            if (b == inst0 || d_stride != 0) stage_matrix(s.D, Db, n);
             D.p = s.D; D.ld = ld_for(n);
         } else {
             D.p = Db; D.ld = n;
@@ -368,17 +440,17 @@ __global__ void moves_kernel(int op, bool o2a, const double *Dg, int64_t d_strid
             best = (op == GNNGLS_OP_TWO_OPT) ? scan_two_opt_o2a(s.tour, n, D, i_fixed, fi != 0, s.red)
                                              : scan_relocate_o2a(s.tour, n, D, i_fixed, fi != 0, s.red);
         } else {
-            best = (op == GNNGLS_OP_TWO_OPT) ? sweep_two_opt_a2a(s.tour, n, D, s.E, fi != 0, s.red)
-                                             : sweep_relocate_a2a(s.tour, n, D, s.E, fi != 0, s.red);
+            best = (op == GNNGLS_OP_TWO_OPT) ? sweep_two_opt_a2a(s.tour, n, D, s.E, fi != 0, s.red, team)
+                                             : sweep_relocate_a2a(s.tour, n, D, s.E, fi != 0, s.red, team);
         }
         const bool found = best.key >= 0;
         const int mi = !found ? -1 : (o2a ? i_fixed : (best.key >> 16));
         const int mj = !found ? -1 : (o2a ? best.key : (best.key & 0xffff));
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && writer) {
             out_delta[b] = found ? best.delta : 0.0;
             out_move[2 * b] = mi; out_move[2 * b + 1] = mj;
         }
-        if (out_tours) {
+        if (out_tours && writer) {
             if (found) apply_move(op, s.tour, s.tmp, mi, mj);
             for (int p = threadIdx.x; p <= n; p += blockDim.x) out_tours[(size_t)b * (n + 1) + p] = s.tour[p];
         }
@@ -386,14 +458,17 @@ __global__ void moves_kernel(int op, bool o2a, const double *Dg, int64_t d_strid
     }
 }
 
-template <bool STAGE_D>
+template <bool STAGE_D, bool CL>
 __global__ void local_search_kernel(const double *Dg, int *tours, double *costs, int B, int n, int fi,
                                     double *events, int *n_events, int max_events, int *status,
                                     long long *counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem s;
     smem_layout(n, STAGE_D, false, false, &s, smem_raw);
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    int inst0, inst_stride;
+    auto team = make_team<CL>(s, &inst0, &inst_stride);
+    const bool writer = team.lead();
+    for (int b = inst0; b < B; b += inst_stride) {
         const double *Db = Dg + (size_t)b * n * n;
         for (int p = threadIdx.x; p <= n; p += blockDim.x) s.tour[p] = tours[(size_t)b * (n + 1) + p];
         MatPlain D;
@@ -401,11 +476,12 @@ __global__ void local_search_kernel(const double *Dg, int *tours, double *costs,
         else { D.p = Db; D.ld = n; }
         if (threadIdx.x == 0) s.slot[0] = costs[b];
         __syncthreads();
-        EventLog log{events ? events + (size_t)b * max_events : nullptr, max_events, 0};
+        EventLog log{(events && writer) ? events + (size_t)b * max_events : nullptr, max_events, 0};
         long long cnt[4] = {0, 0, 0, 0};
-        local_search_dev(s, n, D, fi != 0, &s.slot[0], log, cnt);
-        for (int p = threadIdx.x; p <= n; p += blockDim.x) tours[(size_t)b * (n + 1) + p] = s.tour[p];
-        if (threadIdx.x == 0) {
+        local_search_dev(s, n, D, fi != 0, &s.slot[0], log, cnt, team);
+        // every member has read the instance's tour before the first barrier of the search; member 0 writes it back
+        if (writer) for (int p = threadIdx.x; p <= n; p += blockDim.x) tours[(size_t)b * (n + 1) + p] = s.tour[p];
+        if (threadIdx.x == 0 && writer) {
             costs[b] = s.slot[0];
             if (n_events) n_events[b] = log.count;
             if (status) status[b] = (events && log.count > max_events) ? GNNGLS_INST_EVENTS_TRUNCATED : 0;
@@ -435,8 +511,14 @@ constexpr int kStallCap = 1 << 16;   // safety cap on perturbation-loop trips pe
 
 // algorithms.py:135-195.  STAGED: D (fp64) and the penalties (u16) live in shared memory;
 // otherwise both are read from global memory (L2-resident).
-template <bool STAGED>
+// CL (never with STAGED): one thread-block CLUSTER per instance.  The all-pairs sweeps of every local_search -- all of the
+// O(n^2) work -- are shared by the cluster's CTAs (struct Cluster); the perturbation loop, whose scans are O(n) and which
+// owns the penalties, runs on member 0 alone while the others wait at the cluster barrier and then copy member 0's tour
+// and cost out of its shared memory.  Every member applies the same moves to its replica, so all of them track the
+// same current and best tour; member 0 writes the state back.
+template <bool STAGED, bool CL>
 __global__ void gls_kernel(const GlsDev P) {
+    static_assert(!(STAGED && CL), "the cluster tier reads D and the penalties from global memory");
     const gnngls_gls_args &a = P.a;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n;
@@ -445,8 +527,11 @@ __global__ void gls_kernel(const GlsDev P) {
     const bool fi = a.first_improvement != 0;
     const size_t nn = (size_t)n * n;
     if (threadIdx.x == 0) s.ivars[0] = 0;
+    int inst0, inst_stride;
+    auto team = make_team<CL>(s, &inst0, &inst_stride);
+    const bool lead = team.lead();
 
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    for (int b = inst0; b < a.B; b += inst_stride) {
         const double *Db = a.D + (size_t)b * nn;
         int *pen_g = a.penalties ? a.penalties + (size_t)b * nn : nullptr;
         int status = 0;
@@ -463,7 +548,8 @@ __global__ void gls_kernel(const GlsDev P) {
             }
         } else {
             D.p = Db; D.ld = n;
-            if (!a.resume) for (int idx = threadIdx.x; idx < (int)nn; idx += blockDim.x) pen_g[idx] = 0;
+            // only member 0 ever touches the penalties, so it alone clears them
+            if (!a.resume && lead) for (int idx = threadIdx.x; idx < (int)nn; idx += blockDim.x) pen_g[idx] = 0;
         }
         // slot[0] = cur_cost, slot[1] = best_cost, slot[2] = scratch for tour_cost
         if (threadIdx.x == 0) {
@@ -475,11 +561,11 @@ __global__ void gls_kernel(const GlsDev P) {
         double k;
         if (a.resume) k = a.k[b];
         else k = __ddiv_rn(__dmul_rn(0.1, s.slot[0]), (double)n);                // :137
-        EventLog log{a.events ? a.events + (size_t)b * a.max_events : nullptr, a.max_events, 0};
+        EventLog log{(a.events && lead) ? a.events + (size_t)b * a.max_events : nullptr, a.max_events, 0};
         long long cnt[4] = {0, 0, 0, 0};
 
         if (!a.resume) {
-            local_search_dev(s, n, D, fi, &s.slot[0], log, cnt);                  // :142
+            local_search_dev(s, n, D, fi, &s.slot[0], log, cnt, team);            // :142
             for (int p = threadIdx.x; p <= n; p += blockDim.x) s.best_tour[p] = s.tour[p];   // :143
             if (threadIdx.x == 0) s.slot[1] = s.slot[0];
             __syncthreads();
@@ -497,7 +583,7 @@ __global__ void gls_kernel(const GlsDev P) {
                 guide.vec = static_cast<const float *>(a.guides) + ((size_t)b * a.n_guides + gsel) * (nn - n) / 2;
             }
             int moves = 0, trips = 0;
-            while (moves < a.perturbation_moves) {                                // :151
+            while (lead && moves < a.perturbation_moves) {                        // :151
                 if (++trips > kStallCap) { status |= GNNGLS_INST_STALLED; break; }
                 // ---- :153-159 arg-max utility over tour edges, first edge wins ties
                 Best u;
@@ -555,7 +641,19 @@ __global__ void gls_kernel(const GlsDev P) {
                 }
 #undef GLS_PERTURB
             }
-            local_search_dev(s, n, D, fi, &s.slot[0], log, cnt);                  // :188
+            if constexpr (CL) {
+                // hand member 0's perturbed tour and its cost to the other members.  Member 0 changes neither before
+                // the first barrier of the local search below, which no member reaches before it has finished copying.
+                cg::cluster_group cl = cg::this_cluster();
+                cl.sync();
+                if (!lead) {
+                    const int *t0 = cl.map_shared_rank(s.tour, 0);
+                    for (int p = threadIdx.x; p <= n; p += blockDim.x) s.tour[p] = t0[p];
+                    if (threadIdx.x == 0) s.slot[0] = *cl.map_shared_rank(&s.slot[0], 0);
+                }
+                __syncthreads();
+            }
+            local_search_dev(s, n, D, fi, &s.slot[0], log, cnt, team);            // :188
             if (s.slot[0] < s.slot[1]) {                                          // :190-191 (block-uniform)
                 for (int p = threadIdx.x; p <= n; p += blockDim.x) s.best_tour[p] = s.tour[p];
                 __syncthreads();
@@ -564,13 +662,15 @@ __global__ void gls_kernel(const GlsDev P) {
             __syncthreads();
         }
 
-        // ---- store state
-        for (int p = threadIdx.x; p <= n; p += blockDim.x) {
-            a.cur_tours[(size_t)b * (n + 1) + p] = s.tour[p];
-            a.best_tours[(size_t)b * (n + 1) + p] = s.best_tour[p];
+        // ---- store state (member 0 of a cluster; every member holds the same tours and costs)
+        if (lead) {
+            for (int p = threadIdx.x; p <= n; p += blockDim.x) {
+                a.cur_tours[(size_t)b * (n + 1) + p] = s.tour[p];
+                a.best_tours[(size_t)b * (n + 1) + p] = s.best_tour[p];
+            }
+            if (STAGED && pen_g) for (int idx = threadIdx.x; idx < (int)nn; idx += blockDim.x) pen_g[idx] = s.pen[idx];
         }
-        if (STAGED && pen_g) for (int idx = threadIdx.x; idx < (int)nn; idx += blockDim.x) pen_g[idx] = s.pen[idx];
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && lead) {
             a.cur_costs[b] = s.slot[0];
             a.best_costs[b] = s.slot[1];
             if (!a.resume) a.k[b] = k;
@@ -583,6 +683,8 @@ __global__ void gls_kernel(const GlsDev P) {
         }
         __syncthreads();
     }
+    // no member may exit while another can still read its shared memory
+    if constexpr (CL) cg::this_cluster().sync();
 }
 
 // algorithms.py:9-18 + __init__.py:17-21.  One warp per instance.
@@ -680,6 +782,59 @@ int grid_for(int B) {
     return B < cap ? (B > 0 ? B : 1) : cap;
 }
 
+// Cluster tier (few, large instances).  One CTA per instance leaves most of the GPU idle when B is far below the SM
+// count -- TSP500 x 8 used 8 of 148 SMs -- so the instance's sweeps are shared by a thread-block cluster instead:
+// the largest power of two <= min(16, SMs / B), when that is at least 2 and n is large enough for a sweep to outlast a
+// cluster barrier (~0.2 us).  GNNGLS_CLUSTER=0 disables the tier, GNNGLS_CLUSTER=2|4|8|16 forces a size (tests, A/B).
+constexpr int kClusterMinN = 48;
+
+int cluster_size_for(int B, int n) {
+    int forced = -1;
+    if (const char *e = getenv("GNNGLS_CLUSTER")) forced = atoi(e);
+    if (forced == 0 || forced == 1) return 1;
+    if (forced > 1) {
+        int c = 2;
+        while (c * 2 <= forced && c * 2 <= kMaxCluster) c *= 2;
+        return c;
+    }
+    if (n < kClusterMinN) return 1;
+    const int sms = gnngls::device_sm_count();
+    int c = 1;
+    while (c * 2 <= kMaxCluster && (long long)B * (c * 2) <= sms) c *= 2;
+    // no more members than there are rows to deal: a 128-thread CTA brings 4 warps
+    while (c > 1 && c * (pick_threads(n) / 32) > 2 * n) c /= 2;
+    return c;
+}
+
+// Launches `kernel` with clusters of `csize` CTAs (grid = clusters x csize), as many clusters as instances but no more
+// than can be co-resident.  Falls back to half the size when the device cannot place the cluster (GPCs with fewer SMs).
+template <typename... KArgs, typename... Args>
+int launch_clustered(void (*kernel)(KArgs...), int csize, int B, int threads, size_t smem, cudaStream_t st,
+                     const char *what, Args... args) {
+    GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (smem > 48 * 1024)
+        GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (; csize >= 2; csize /= 2) {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cfg.gridDim = dim3(csize);
+        int max_clusters = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg);
+        if (e != cudaSuccess || max_clusters < 1) { (void)cudaGetLastError(); continue; }
+        const int clusters = B < max_clusters ? B : max_clusters;
+        cfg.gridDim = dim3(clusters * csize);
+        e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+        if (e == cudaSuccess) return GNNGLS_OK;
+        (void)cudaGetLastError();
+    }
+    ::gnngls::set_error("launch of %s failed: no cluster size could be placed", what);
+    return GNNGLS_ERR_CUDA;
+}
+
 int check_n(int n) {
     GNNGLS_REQUIRE(n >= 3 && n <= 1024, GNNGLS_ERR_UNSUPPORTED, "n=%d outside supported range [3,1024]", n);
     return GNNGLS_OK;
@@ -698,13 +853,17 @@ int launch_moves(int op, bool o2a, const double *D, int64_t stride, const int *t
     const size_t limit = (size_t)gnngls::device_max_optin_smem();
     // One sweep per instance does not amortise staging an n x n fp64 matrix into shared memory (measured: 6x slower at
     // n=100); stage only a matrix shared by the whole batch.  local_search / GLS, which sweep many times, always stage.
+    const int csize = o2a ? 1 : cluster_size_for(B, n);
+    if (csize > 1)
+        return launch_clustered(moves_kernel<false, true>, csize, B, threads, plain, st, "moves_kernel (cluster)", op, o2a,
+                                D, stride, tours, pos, B, n, fi, out_delta, out_move, out_tours);
     if (stride == 0 && staged <= limit) {
-        if (int rc = ensure_smem(moves_kernel<true>, staged)) return rc;
-        moves_kernel<true><<<grid_for(B), threads, staged, st>>>(op, o2a, D, stride, tours, pos, B, n, fi, out_delta,
-                                                                out_move, out_tours);
+        if (int rc = ensure_smem(moves_kernel<true, false>, staged)) return rc;
+        moves_kernel<true, false><<<grid_for(B), threads, staged, st>>>(op, o2a, D, stride, tours, pos, B, n, fi,
+                                                                       out_delta, out_move, out_tours);
     } else {
-        moves_kernel<false><<<grid_for(B), threads, plain, st>>>(op, o2a, D, stride, tours, pos, B, n, fi, out_delta,
-                                                                out_move, out_tours);
+        moves_kernel<false, false><<<grid_for(B), threads, plain, st>>>(op, o2a, D, stride, tours, pos, B, n, fi,
+                                                                        out_delta, out_move, out_tours);
     }
     GNNGLS_LAUNCH_OK("moves_kernel");
     return GNNGLS_OK;
@@ -737,13 +896,18 @@ extern "C" int gnngls_local_search_batch(const double *D, int32_t *tours, double
     const int threads = pick_threads(n);
     const size_t staged = smem_layout(n, true, false, false, nullptr, nullptr);
     const size_t plain = smem_layout(n, false, false, false, nullptr, nullptr);
+    const int csize = cluster_size_for(B, n);
+    if (csize > 1)
+        return launch_clustered(local_search_kernel<false, true>, csize, B, threads, plain, st,
+                                "local_search_kernel (cluster)", D, tours, costs, B, n, first_improvement, events, n_events,
+                                max_events, status, reinterpret_cast<long long *>(counters));
     if (staged <= (size_t)gnngls::device_max_optin_smem()) {
-        if (int rc = ensure_smem(local_search_kernel<true>, staged)) return rc;
-        local_search_kernel<true><<<grid_for(B), threads, staged, st>>>(
+        if (int rc = ensure_smem(local_search_kernel<true, false>, staged)) return rc;
+        local_search_kernel<true, false><<<grid_for(B), threads, staged, st>>>(
             D, tours, costs, B, n, first_improvement, events, n_events, max_events, status,
             reinterpret_cast<long long *>(counters));
     } else {
-        local_search_kernel<false><<<grid_for(B), threads, plain, st>>>(
+        local_search_kernel<false, false><<<grid_for(B), threads, plain, st>>>(
             D, tours, costs, B, n, first_improvement, events, n_events, max_events, status,
             reinterpret_cast<long long *>(counters));
     }
@@ -782,13 +946,16 @@ extern "C" int gnngls_gls_batch(const gnngls_gls_args *args, void *stream) {
     if (tier < 0) { const char *e = getenv("GNNGLS_GLS_TIER"); tier = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'g' ? 2 : 0)); }
     const bool fits = staged <= (size_t)gnngls::device_max_optin_smem();
     const bool use_global = a.penalties && (tier == 2 || (tier == 0 && a.n >= 64)) ;
+    const int csize = a.penalties ? cluster_size_for(a.B, a.n) : 1;   // the cluster tier keeps the penalties in global memory
+    if (csize > 1)
+        return launch_clustered(gls_kernel<false, true>, csize, a.B, threads, plain, st, "gls_kernel (cluster)", P);
     if (fits && !use_global) {
-        if (int rc = ensure_smem(gls_kernel<true>, staged)) return rc;
-        gls_kernel<true><<<grid_for(a.B), threads, staged, st>>>(P);
+        if (int rc = ensure_smem(gls_kernel<true, false>, staged)) return rc;
+        gls_kernel<true, false><<<grid_for(a.B), threads, staged, st>>>(P);
     } else {
         GNNGLS_REQUIRE(a.penalties, GNNGLS_ERR_WORKSPACE,
                        "n=%d does not fit shared memory: a [B,n,n] int32 penalties buffer is required", a.n);
-        gls_kernel<false><<<grid_for(a.B), threads, plain, st>>>(P);
+        gls_kernel<false, false><<<grid_for(a.B), threads, plain, st>>>(P);
     }
     GNNGLS_LAUNCH_OK("gls_kernel");
     return GNNGLS_OK;

@@ -198,6 +198,53 @@ def test_nn_ls_gls_batch_vs_oracle(n, B, K):
     assert np.array_equal(cnt[:, 0] + cnt[:, 1], o_cnt[:, 0]) and np.array_equal(cnt[:, 2], o_cnt[:, 1])
 
 
+@pytest.mark.parametrize('n,B,K,csize', [(48, 3, 4, 2), (64, 5, 3, 8), (100, 3, 3, 16), (100, 40, 2, 4), (101, 7, 2, 16),
+                                         (170, 2, 1, 2), (200, 9, 2, 16), (500, 1, 1, 16)])
+@pytest.mark.parametrize('fi', [False, True])
+def test_cluster_tier_bit_identical(n, B, K, csize, fi, monkeypatch):
+    """One thread-block cluster per instance (north star (4)) against one CTA per instance and
+    against the CPU oracle: sweeps, local_search and GLS -- tours, costs, event logs, penalties and counters bit-exact
+    whatever the cluster size.  B=40 with clusters of 4 makes the clusters loop over instances."""
+    rng = np.random.default_rng(31 * n + B)
+    _, D = instances.random_instances(B, n, seed=11 * n + 1)
+    if n == 101:
+        D = np.round(D * 8.0) / 8.0                                   # many exact ties: the (delta, rank) order decides
+    N = n * (n - 1) // 2
+    regret = np.maximum(rng.random((B, N)).astype(np.float32) - np.float32(0.4), 0).astype(np.float32)
+    Dd, rd = dev(D), dev(regret)
+    rt = dev(random_tours(rng, B, n))
+
+    def run():
+        out = {}
+        for op in (_ops.OP_TWO_OPT, _ops.OP_RELOCATE):
+            d, m, t = _ops.moves_eval(op, Dd, rt, None, fi)
+            out['mv%d' % op] = (d.cpu().numpy(), m.cpu().numpy(), t.cpu().numpy())
+        tours, costs = algorithms.nearest_neighbor_batch(rd, Dd)
+        lt, lc, li = algorithms.local_search_batch(tours, costs, Dd, first_improvement=fi, max_events=4096)
+        out['ls'] = (lt.cpu().numpy(), lc.cpu().numpy(), li['events'].cpu().numpy(), li['n_events'].cpu().numpy())
+        bt, bc, info = algorithms.guided_local_search_batch(Dd, rd.view(B, 1, N), tours, costs, K, perturbation_moves=20,
+                                                            first_improvement=fi, max_events=16384, keep_penalties=True)
+        assert int(info['status'].max()) == 0
+        out['gls'] = (bt.cpu().numpy(), bc.cpu().numpy(), info['events'].cpu().numpy(), info['n_events'].cpu().numpy(),
+                      info['state'].penalties.cpu().numpy(), info['counters'].cpu().numpy())
+        return out
+
+    monkeypatch.setenv('GNNGLS_CLUSTER', '0')
+    solo = run()
+    monkeypatch.setenv('GNNGLS_CLUSTER', str(csize))
+    clus = run()
+    for key in solo:
+        for x, y in zip(solo[key], clus[key]):
+            if x.dtype.kind == 'f':
+                assert np.array_equal(_golden.bits(x), _golden.bits(y)), (key, n, B, csize)
+            else:
+                assert np.array_equal(x, y), (key, n, B, csize)
+    if not fi:
+        o_t, o_c = gls_port.pipeline_batch(D, regret, K, 20, nthreads=4)[:2]
+        assert np.array_equal(clus['gls'][0], np.asarray(o_t))
+        assert np.array_equal(_golden.bits(clus['gls'][1]), _golden.bits(np.asarray(o_c)))
+
+
 def test_gls_matrix_guides_alternating_and_first_improvement():
     n, B, K = 30, 16, 5
     rng = np.random.default_rng(9)
