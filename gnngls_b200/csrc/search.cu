@@ -12,6 +12,8 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 #include <cooperative_groups.h>
 #include "common.h"
 
@@ -99,6 +101,7 @@ struct Solo {
     __device__ __forceinline__ int row_stride(int nw) const { return nw; }
     __device__ __forceinline__ Best reduce(Best v, bool fi, Best *red) { return block_reduce_best(v, fi, red); }
     __device__ __forceinline__ bool lead() const { return true; }
+    static constexpr bool kDeep = false;
 };
 
 // Every CTA of the cluster holds a replica of the tour; each sweeps its share of the rows, writes its winner into
@@ -112,6 +115,9 @@ struct Cluster {
     __device__ __forceinline__ int first_row(int warp) const { return warp * size + rank; }
     __device__ __forceinline__ int row_stride(int nw) const { return nw * size; }
     __device__ __forceinline__ bool lead() const { return rank == 0; }   // the member that owns the global results
+    // D comes from L2 (cluster barriers invalidate L1) and a warp owns only one or two rows: keep four candidates'
+    // worth of gathers in flight per lane
+    static constexpr bool kDeep = true;
     __device__ Best reduce(Best v, bool fi, Best *red) {
         v = block_reduce_best(v, fi, red);
         cg::cluster_group cl = cg::this_cluster();
@@ -161,7 +167,22 @@ __device__ Best sweep_two_opt_a2a(const int *t, int n, const M &D, double *E, bo
     for (int i = 1 + team.first_row(warp); i <= n - 3; i += team.row_stride(nw)) {
         const int a = t[i], b = t[i - 1];
         const double Ei = E[i];
-        for (int j = i + 2 + lane; j <= n - 1; j += 32) {
+        int j = i + 2 + lane;
+        if constexpr (T::kDeep) {
+            for (; j + 96 <= n - 1; j += 128) {
+                double x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = D(a, t[j + 32 * u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = __dadd_rn(x[u], D(b, t[j + 32 * u - 1]));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    x[u] = __dsub_rn(__dsub_rn(x[u], Ei), E[j + 32 * u]);
+                    consider(best, x[u], (i << 16) | (j + 32 * u), fi);
+                }
+            }
+        }
+        for (; j <= n - 1; j += 32) {
             const int c = t[j], d = t[j - 1];
             double x = __dadd_rn(D(a, c), D(b, d));
             x = __dsub_rn(x, Ei);
@@ -186,7 +207,30 @@ __device__ Best sweep_relocate_a2a(const int *t, int n, const M &D, double *E, b
         const int a = t[i - 1], b = t[i], c = t[i + 1];
         double base = __dsub_rn(-E[i - 1], E[i]);
         base = __dadd_rn(base, D(a, c));
-        for (int j = 1 + lane; j <= n - 1; j += 32) {
+        int j = 1 + lane;
+        if constexpr (T::kDeep) {
+            for (; j + 96 <= n - 1; j += 128) {
+                double x[4], y[4];
+                int q[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ju = j + 32 * u;
+                    q[u] = (i < ju) ? ju : ju - 1;           // ju in {i, i-1} is evaluated (valid indices) and dropped below
+                    x[u] = D(t[q[u]], b);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) y[u] = D(b, t[q[u] + 1]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ju = j + 32 * u;
+                    double z = __dsub_rn(base, E[q[u]]);
+                    z = __dadd_rn(z, x[u]);
+                    z = __dadd_rn(z, y[u]);
+                    if (ju != i && ju != i - 1) consider(best, z, (i << 16) | ju, fi);
+                }
+            }
+        }
+        for (; j <= n - 1; j += 32) {
             if (j == i || j == i - 1) continue;   // permutations(.,2) has no i==j; operators.py:135 skips i-j==1
             const int q = (i < j) ? j : j - 1;
             const int d = t[q], e = t[q + 1];
@@ -403,7 +447,7 @@ __device__ __forceinline__ typename TeamOf<CL>::type make_team(const Smem &s, in
 }
 
 template <bool STAGE_D, bool CL>
-__global__ void moves_kernel(int op, bool o2a, const double *Dg, int64_t d_stride, const int *tours,
+__device__ __forceinline__ void moves_body(int op, bool o2a, const double *Dg, int64_t d_stride, const int *tours,
                              const int *pos, int B, int n, int fi, double *out_delta, int *out_move,
                              int *out_tours) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -459,7 +503,7 @@ __global__ void moves_kernel(int op, bool o2a, const double *Dg, int64_t d_strid
 }
 
 template <bool STAGE_D, bool CL>
-__global__ void local_search_kernel(const double *Dg, int *tours, double *costs, int B, int n, int fi,
+__device__ __forceinline__ void local_search_body(const double *Dg, int *tours, double *costs, int B, int n, int fi,
                                     double *events, int *n_events, int max_events, int *status,
                                     long long *counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -517,7 +561,7 @@ constexpr int kStallCap = 1 << 16;   // safety cap on perturbation-loop trips pe
 // and cost out of its shared memory.  Every member applies the same moves to its replica, so all of them track the
 // same current and best tour; member 0 writes the state back.
 template <bool STAGED, bool CL>
-__global__ void gls_kernel(const GlsDev P) {
+__device__ __forceinline__ void gls_body(const GlsDev &P) {
     static_assert(!(STAGED && CL), "the cluster tier reads D and the penalties from global memory");
     const gnngls_gls_args &a = P.a;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -687,6 +731,32 @@ __global__ void gls_kernel(const GlsDev P) {
     if constexpr (CL) cg::this_cluster().sync();
 }
 
+// Kernel entry points.  The one-CTA tiers keep the compiler's own register choice (48 registers for the L2-resident GLS
+// tier: five CTAs of 256 threads per SM); the cluster tier is bounded for CTAs of up to 1024 threads.
+template <bool STAGE_D>
+__global__ void moves_kernel(int op, bool o2a, const double *Dg, int64_t d_stride, const int *tours, const int *pos, int B,
+                             int n, int fi, double *out_delta, int *out_move, int *out_tours) {
+    moves_body<STAGE_D, false>(op, o2a, Dg, d_stride, tours, pos, B, n, fi, out_delta, out_move, out_tours);
+}
+__global__ void __launch_bounds__(1024) moves_cluster_kernel(int op, bool o2a, const double *Dg, int64_t d_stride,
+                                                             const int *tours, const int *pos, int B, int n, int fi,
+                                                             double *out_delta, int *out_move, int *out_tours) {
+    moves_body<false, true>(op, o2a, Dg, d_stride, tours, pos, B, n, fi, out_delta, out_move, out_tours);
+}
+template <bool STAGE_D>
+__global__ void local_search_kernel(const double *Dg, int *tours, double *costs, int B, int n, int fi, double *events,
+                                    int *n_events, int max_events, int *status, long long *counters) {
+    local_search_body<STAGE_D, false>(Dg, tours, costs, B, n, fi, events, n_events, max_events, status, counters);
+}
+__global__ void __launch_bounds__(1024) local_search_cluster_kernel(const double *Dg, int *tours, double *costs, int B,
+                                                                    int n, int fi, double *events, int *n_events,
+                                                                    int max_events, int *status, long long *counters) {
+    local_search_body<false, true>(Dg, tours, costs, B, n, fi, events, n_events, max_events, status, counters);
+}
+template <bool STAGED>
+__global__ void gls_kernel(const GlsDev P) { gls_body<STAGED, false>(P); }
+__global__ void __launch_bounds__(1024) gls_cluster_kernel(const GlsDev P) { gls_body<false, true>(P); }
+
 // algorithms.py:9-18 + __init__.py:17-21.  One warp per instance.
 __global__ void nn_init_kernel(int guide_kind, const void *guides, const double *Dg, int B, int n, int depot,
                                int *out_tours, double *out_costs) {
@@ -740,6 +810,72 @@ __global__ void nn_init_kernel(int guide_kind, const void *guides, const double 
     }
 }
 
+// The same constructor with one CTA per instance, one candidate node per thread (n <= 1024): for a handful of large instances
+// the n-1 dependent steps are the whole cost, and a step is then one guide load + one (value, node) reduction with a single
+// block barrier (the warps' partial minima are double buffered by step parity and combined redundantly by every warp).
+__global__ void __launch_bounds__(1024) nn_init_block_kernel(int guide_kind, const void *guides, const double *Dg, int B,
+                                                             int n, int depot, int *out_tours, double *out_costs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *E = reinterpret_cast<double *>(smem_raw);                        // n + 1
+    double *pw = E + (n + 1);                                                // 2 x 32 partial minima
+    int *pj = reinterpret_cast<int *>(pw + 64);                              // 2 x 32 their nodes
+    int *tour = pj + 64;                                                     // n + 1
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int j = threadIdx.x;
+    const size_t nn = (size_t)n * n;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        GuideRef g;
+        g.n = n;
+        g.mat = guide_kind == GNNGLS_GUIDE_MATRIX_F64 ? static_cast<const double *>(guides) + (size_t)b * nn : nullptr;
+        g.vec = guide_kind == GNNGLS_GUIDE_MATRIX_F64 ? nullptr : static_cast<const float *>(guides) + (size_t)b * (nn - n) / 2;
+        bool visited = (j >= n) || (j == depot);
+        int cur = depot;
+        if (threadIdx.x == 0) { tour[0] = depot; tour[n] = depot; }
+        for (int len = 1; len < n; ++len) {
+            double bw = 0.0;
+            int bj = -1;
+            if (!visited) {
+                bw = g(cur, j);
+                if (bw != bw) bw = INFINITY;                                  // NaN guide values: keep the comparison a total order
+                bj = j;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ow = __shfl_xor_sync(0xffffffffu, bw, off);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+                if (oj >= 0 && (bj < 0 || ow < bw || (ow == bw && oj < bj))) { bw = ow; bj = oj; }
+            }
+            const int par = (len & 1) * 32;
+            if (lane == 0) { pw[par + warp] = bw; pj[par + warp] = bj; }
+            __syncthreads();
+            bw = 0.0; bj = -1;
+            if (lane < nw) { bw = pw[par + lane]; bj = pj[par + lane]; }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ow = __shfl_xor_sync(0xffffffffu, bw, off);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+                if (oj >= 0 && (bj < 0 || ow < bw || (ow == bw && oj < bj))) { bw = ow; bj = oj; }
+            }
+            if (bj == j) visited = true;
+            if (threadIdx.x == 0) tour[len] = bj;
+            cur = bj;
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p <= n; p += blockDim.x) out_tours[(size_t)b * (n + 1) + p] = tour[p];
+        if (Dg && out_costs) {
+            const double *Db = Dg + (size_t)b * nn;
+            for (int p = threadIdx.x; p < n; p += blockDim.x) E[p] = Db[(size_t)tour[p] * n + tour[p + 1]];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double c = 0.0;
+                for (int p = 0; p < n; ++p) c = __dadd_rn(c, E[p]);
+                out_costs[b] = c;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void tour_cost_kernel(const double *Dg, const int *tours, int B, int n, double *out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -783,56 +919,96 @@ int grid_for(int B) {
 }
 
 // Cluster tier (few, large instances).  One CTA per instance leaves most of the GPU idle when B is far below the SM
-// count -- TSP500 x 8 used 8 of 148 SMs -- so the instance's sweeps are shared by a thread-block cluster instead:
-// the largest power of two <= min(16, SMs / B), when that is at least 2 and n is large enough for a sweep to outlast a
-// cluster barrier (~0.2 us).  GNNGLS_CLUSTER=0 disables the tier, GNNGLS_CLUSTER=2|4|8|16 forces a size (tests, A/B).
+// count -- TSP500 x 8 used 8 of 148 SMs -- so the instance's sweeps are shared by a thread-block cluster instead.
+// cluster_limit_for() gives the largest size worth trying: the largest power of two <= min(16, 2 SMs / B) (CTAs of the
+// cluster tier have at most 512 threads, two fit an SM), when that is at least 2 and n is large enough for a sweep to
+// outlast a cluster barrier (~0.2 us); launch_clustered() then picks, among the sizes up to that limit, the one that
+// finishes the batch in the fewest (rounds of co-resident clusters) / (cluster size).
+// GNNGLS_CLUSTER=0 disables the tier, GNNGLS_CLUSTER=2|4|8|16 forces a size (tests, A/B).
 constexpr int kClusterMinN = 48;
+constexpr int kClusterMaxThreads = 512;
 
-int cluster_size_for(int B, int n) {
+int cluster_threads(int n) { const int t = pick_threads(n); return t < kClusterMaxThreads ? t : kClusterMaxThreads; }
+
+// > 0: upper limit chosen by the policy; < 0: -(forced size); 1: one CTA per instance
+int cluster_limit_for(int B, int n) {
     int forced = -1;
     if (const char *e = getenv("GNNGLS_CLUSTER")) forced = atoi(e);
     if (forced == 0 || forced == 1) return 1;
     if (forced > 1) {
         int c = 2;
         while (c * 2 <= forced && c * 2 <= kMaxCluster) c *= 2;
-        return c;
+        return -c;
     }
     if (n < kClusterMinN) return 1;
     const int sms = gnngls::device_sm_count();
     int c = 1;
-    while (c * 2 <= kMaxCluster && (long long)B * (c * 2) <= sms) c *= 2;
-    // no more members than there are rows to deal: a 128-thread CTA brings 4 warps
-    while (c > 1 && c * (pick_threads(n) / 32) > 2 * n) c /= 2;
+    while (c * 2 <= kMaxCluster && (long long)B * (c * 2) <= 2LL * sms) c *= 2;
+    // no more members than there are rows to deal
+    while (c > 1 && c * (cluster_threads(n) / 32) > 2 * n) c /= 2;
     return c;
 }
 
-// Launches `kernel` with clusters of `csize` CTAs (grid = clusters x csize), as many clusters as instances but no more
-// than can be co-resident.  Falls back to half the size when the device cannot place the cluster (GPCs with fewer SMs).
+// how many clusters of `csize` CTAs of this kernel can be resident at once (0: cannot be placed); cached
+int max_active_clusters(const void *kernel, int csize, int threads, size_t smem) {
+    struct Key { const void *k; int c, t; size_t s; int dev; int val; };
+    static std::mutex mu;
+    static std::vector<Key> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> g(mu);
+        for (const Key &e : cache)
+            if (e.k == kernel && e.c == csize && e.t == threads && e.s == smem && e.dev == dev) return e.val;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.gridDim = dim3(csize);
+    int mc = 0;
+    if (cudaOccupancyMaxActiveClusters(&mc, kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); mc = 0; }
+    std::lock_guard<std::mutex> g(mu);
+    cache.push_back(Key{kernel, csize, threads, smem, dev, mc});
+    return mc;
+}
+
+// Launches `kernel` with clusters of CTAs (grid = clusters x size), as many clusters as instances but no more than can be
+// co-resident (the kernels loop over instances).  `limit` comes from cluster_limit_for().  Among the cluster sizes up to the
+// limit and CTA sizes (the one-CTA tier's, or 512 threads so that two CTAs share an SM) the launch takes the combination
+// with the smallest (rounds of co-resident clusters) / (threads per instance).
 template <typename... KArgs, typename... Args>
-int launch_clustered(void (*kernel)(KArgs...), int csize, int B, int threads, size_t smem, cudaStream_t st,
+int launch_clustered(void (*kernel)(KArgs...), int limit, int B, int n, size_t smem, cudaStream_t st,
                      const char *what, Args... args) {
     GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     if (smem > 48 * 1024)
         GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (; csize >= 2; csize /= 2) {
-        cudaLaunchConfig_t cfg = {};
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cfg.gridDim = dim3(csize);
-        int max_clusters = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg);
-        if (e != cudaSuccess || max_clusters < 1) { (void)cudaGetLastError(); continue; }
-        const int clusters = B < max_clusters ? B : max_clusters;
-        cfg.gridDim = dim3(clusters * csize);
-        e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-        if (e == cudaSuccess) return GNNGLS_OK;
-        (void)cudaGetLastError();
+    const void *kp = reinterpret_cast<const void *>(kernel);
+    const int t_full = pick_threads(n), t_half = cluster_threads(n);
+    int best_c = 0, best_mc = 0, best_t = 0;
+    double best_score = 0.0;
+    for (int threads = t_full; threads >= t_half; threads = (threads == t_half ? 0 : t_half)) {
+        for (int c = limit < 0 ? -limit : limit; c >= 2; c /= 2) {
+            const int mc = max_active_clusters(kp, c, threads, smem);
+            if (mc < 1) continue;
+            const int rounds = (B + mc - 1) / mc;
+            const double score = (double)rounds / ((double)c * threads);
+            // ties go to the smaller CTA: two of them share an SM's L1 and registers more evenly than one large one
+            if (!best_c || score <= best_score) { best_c = c; best_mc = mc; best_t = threads; best_score = score; }
+            if (limit < 0) break;                      // forced: that size, or the next smaller one that can be placed
+        }
     }
-    ::gnngls::set_error("launch of %s failed: no cluster size could be placed", what);
-    return GNNGLS_ERR_CUDA;
+    GNNGLS_REQUIRE(best_c >= 2, GNNGLS_ERR_CUDA, "launch of %s failed: no cluster size could be placed", what);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = best_c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(best_t); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3((B < best_mc ? B : best_mc) * best_c);
+    GNNGLS_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+    return GNNGLS_OK;
 }
 
 int check_n(int n) {
@@ -853,16 +1029,16 @@ int launch_moves(int op, bool o2a, const double *D, int64_t stride, const int *t
     const size_t limit = (size_t)gnngls::device_max_optin_smem();
     // One sweep per instance does not amortise staging an n x n fp64 matrix into shared memory (measured: 6x slower at
     // n=100); stage only a matrix shared by the whole batch.  local_search / GLS, which sweep many times, always stage.
-    const int csize = o2a ? 1 : cluster_size_for(B, n);
-    if (csize > 1)
-        return launch_clustered(moves_kernel<false, true>, csize, B, threads, plain, st, "moves_kernel (cluster)", op, o2a,
+    const int csize = o2a ? 1 : cluster_limit_for(B, n);
+    if (csize != 1)
+        return launch_clustered(moves_cluster_kernel, csize, B, n, plain, st, "moves_cluster_kernel", op, o2a,
                                 D, stride, tours, pos, B, n, fi, out_delta, out_move, out_tours);
     if (stride == 0 && staged <= limit) {
-        if (int rc = ensure_smem(moves_kernel<true, false>, staged)) return rc;
-        moves_kernel<true, false><<<grid_for(B), threads, staged, st>>>(op, o2a, D, stride, tours, pos, B, n, fi,
+        if (int rc = ensure_smem(moves_kernel<true>, staged)) return rc;
+        moves_kernel<true><<<grid_for(B), threads, staged, st>>>(op, o2a, D, stride, tours, pos, B, n, fi,
                                                                        out_delta, out_move, out_tours);
     } else {
-        moves_kernel<false, false><<<grid_for(B), threads, plain, st>>>(op, o2a, D, stride, tours, pos, B, n, fi,
+        moves_kernel<false><<<grid_for(B), threads, plain, st>>>(op, o2a, D, stride, tours, pos, B, n, fi,
                                                                         out_delta, out_move, out_tours);
     }
     GNNGLS_LAUNCH_OK("moves_kernel");
@@ -896,18 +1072,18 @@ extern "C" int gnngls_local_search_batch(const double *D, int32_t *tours, double
     const int threads = pick_threads(n);
     const size_t staged = smem_layout(n, true, false, false, nullptr, nullptr);
     const size_t plain = smem_layout(n, false, false, false, nullptr, nullptr);
-    const int csize = cluster_size_for(B, n);
-    if (csize > 1)
-        return launch_clustered(local_search_kernel<false, true>, csize, B, threads, plain, st,
-                                "local_search_kernel (cluster)", D, tours, costs, B, n, first_improvement, events, n_events,
+    const int csize = cluster_limit_for(B, n);
+    if (csize != 1)
+        return launch_clustered(local_search_cluster_kernel, csize, B, n, plain, st,
+                                "local_search_cluster_kernel", D, tours, costs, B, n, first_improvement, events, n_events,
                                 max_events, status, reinterpret_cast<long long *>(counters));
     if (staged <= (size_t)gnngls::device_max_optin_smem()) {
-        if (int rc = ensure_smem(local_search_kernel<true, false>, staged)) return rc;
-        local_search_kernel<true, false><<<grid_for(B), threads, staged, st>>>(
+        if (int rc = ensure_smem(local_search_kernel<true>, staged)) return rc;
+        local_search_kernel<true><<<grid_for(B), threads, staged, st>>>(
             D, tours, costs, B, n, first_improvement, events, n_events, max_events, status,
             reinterpret_cast<long long *>(counters));
     } else {
-        local_search_kernel<false, false><<<grid_for(B), threads, plain, st>>>(
+        local_search_kernel<false><<<grid_for(B), threads, plain, st>>>(
             D, tours, costs, B, n, first_improvement, events, n_events, max_events, status,
             reinterpret_cast<long long *>(counters));
     }
@@ -946,16 +1122,17 @@ extern "C" int gnngls_gls_batch(const gnngls_gls_args *args, void *stream) {
     if (tier < 0) { const char *e = getenv("GNNGLS_GLS_TIER"); tier = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'g' ? 2 : 0)); }
     const bool fits = staged <= (size_t)gnngls::device_max_optin_smem();
     const bool use_global = a.penalties && (tier == 2 || (tier == 0 && a.n >= 64)) ;
-    const int csize = a.penalties ? cluster_size_for(a.B, a.n) : 1;   // the cluster tier keeps the penalties in global memory
-    if (csize > 1)
-        return launch_clustered(gls_kernel<false, true>, csize, a.B, threads, plain, st, "gls_kernel (cluster)", P);
+    const int csize = a.penalties ? cluster_limit_for(a.B, a.n) : 1;   // the cluster tier keeps the penalties in global memory
+    if (csize != 1)
+        return launch_clustered(gls_cluster_kernel, csize, a.B, a.n, plain, st,
+                                "gls_cluster_kernel", P);
     if (fits && !use_global) {
-        if (int rc = ensure_smem(gls_kernel<true, false>, staged)) return rc;
-        gls_kernel<true, false><<<grid_for(a.B), threads, staged, st>>>(P);
+        if (int rc = ensure_smem(gls_kernel<true>, staged)) return rc;
+        gls_kernel<true><<<grid_for(a.B), threads, staged, st>>>(P);
     } else {
         GNNGLS_REQUIRE(a.penalties, GNNGLS_ERR_WORKSPACE,
                        "n=%d does not fit shared memory: a [B,n,n] int32 penalties buffer is required", a.n);
-        gls_kernel<false, false><<<grid_for(a.B), threads, plain, st>>>(P);
+        gls_kernel<false><<<grid_for(a.B), threads, plain, st>>>(P);
     }
     GNNGLS_LAUNCH_OK("gls_kernel");
     return GNNGLS_OK;
@@ -969,6 +1146,15 @@ extern "C" int gnngls_nn_init_batch(int guide_kind, const void *guide, const dou
     GNNGLS_REQUIRE(n >= 2 && n <= 1024, GNNGLS_ERR_UNSUPPORTED, "n=%d outside supported range [2,1024]", n);
     GNNGLS_REQUIRE(depot >= 0 && depot < n, GNNGLS_ERR_BAD_ARG, "depot out of range");
     if (B <= 0) return GNNGLS_OK;
+    // few large instances: one CTA per instance (same condition as the cluster tier of the search kernels)
+    if (n >= kClusterMinN && cluster_limit_for(B, n) != 1) {
+        const int threads = (n + 31) / 32 * 32;
+        const size_t smem_b = sizeof(double) * (n + 1 + 64) + sizeof(int) * (64 + n + 1) + 16;
+        nn_init_block_kernel<<<B, threads, smem_b, static_cast<cudaStream_t>(stream)>>>(guide_kind, guide, D, B, n, depot,
+                                                                                      out_tours, out_costs);
+        GNNGLS_LAUNCH_OK("nn_init_block_kernel");
+        return GNNGLS_OK;
+    }
     const int wpb = 4;
     const size_t smem = (sizeof(double) + sizeof(int)) * (size_t)wpb * (n + 1) + 16;
     if (int rc = ensure_smem(nn_init_kernel, smem)) return rc;

@@ -220,6 +220,7 @@ def test_cluster_tier_bit_identical(n, B, K, csize, fi, monkeypatch):
             d, m, t = _ops.moves_eval(op, Dd, rt, None, fi)
             out['mv%d' % op] = (d.cpu().numpy(), m.cpu().numpy(), t.cpu().numpy())
         tours, costs = algorithms.nearest_neighbor_batch(rd, Dd)
+        out['nn'] = (tours.cpu().numpy(), costs.cpu().numpy())
         lt, lc, li = algorithms.local_search_batch(tours, costs, Dd, first_improvement=fi, max_events=4096)
         out['ls'] = (lt.cpu().numpy(), lc.cpu().numpy(), li['events'].cpu().numpy(), li['n_events'].cpu().numpy())
         bt, bc, info = algorithms.guided_local_search_batch(Dd, rd.view(B, 1, N), tours, costs, K, perturbation_moves=20,
