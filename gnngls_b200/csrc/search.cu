@@ -111,7 +111,14 @@ struct Solo {
 // read two barriers ago.
 struct Cluster {
     int rank, size, parity;
-    Best *xch;   // [2][kMaxCluster] in this CTA's shared memory
+    Best *xch;      // [2][kMaxCluster] in this CTA's shared memory
+    // Row cache (large n): a lane's gather D[a][t[j]] touches a different 128-byte line for almost every lane, and the L1 tag
+    // stage serves about one line per cycle -- at n = 500 that, not latency or bandwidth, is what a sweep costs (ncu: 26 sectors
+    // per request).  So a warp first copies the one or two matrix rows its scan row needs into shared memory with coalesced
+    // loads (2 lines per instruction) and gathers from there.  `symmetric` (D[a][b] == D[b][a] bitwise, checked once per
+    // instance) lets relocate take its column term D[d][b] from row b as well.
+    double *rows;   // [warps][2][n] or null
+    int symmetric;
     __device__ __forceinline__ int first_row(int warp) const { return warp * size + rank; }
     __device__ __forceinline__ int row_stride(int nw) const { return nw * size; }
     __device__ __forceinline__ bool lead() const { return rank == 0; }   // the member that owns the global results
@@ -124,8 +131,19 @@ struct Cluster {
         Best *mine = xch + parity * kMaxCluster;
         if ((int)threadIdx.x < size) *cl.map_shared_rank(mine + rank, threadIdx.x) = v;
         cl.sync();
-        Best w = mine[0];
-        for (int q = 1; q < size; ++q) w = pick(w, mine[q], fi);
+        Best w;                                                // every warp combines the (at most 16) winners itself
+        w.delta = 0.0; w.key = -1; w.pad = 0;
+        const int lane = threadIdx.x & 31;
+        if (lane < size) w = mine[lane];
+#pragma unroll
+        for (int off = kMaxCluster / 2; off > 0; off >>= 1) {
+            Best o;
+            o.delta = __shfl_xor_sync(0xffffffffu, w.delta, off);
+            o.key = __shfl_xor_sync(0xffffffffu, w.key, off);
+            w = pick(w, o, fi);
+        }
+        w.delta = __shfl_sync(0xffffffffu, w.delta, 0);
+        w.key = __shfl_sync(0xffffffffu, w.key, 0);
         parity ^= 1;
         return w;
     }
@@ -152,6 +170,28 @@ struct MatPen {
     }
 };
 
+// row cache plumbing: a warp copies one matrix row into its shared-memory buffer with asynchronous 8-byte copies (rows of an
+// odd-n matrix are only 8-byte aligned), all in flight at once: one L2 round trip per row instead of one per candidate
+__device__ __forceinline__ void stage_row_async(double *dst, const double *src, int n, int lane) {
+    if ((n & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {   // (warp-uniform)
+        for (int c = 2 * lane; c < n; c += 64) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst + c);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + c) : "memory");
+        }
+        return;
+    }
+    for (int c = lane; c < n; c += 32) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst + c);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + c) : "memory");
+    }
+}
+__device__ __forceinline__ void stage_elem_async(double *dst, const double *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // all-pairs sweeps (operators.py:32-50, :129-147): one warp per row i, lanes over j
 // ----------------------------------------------------------------------------------------------
@@ -159,11 +199,56 @@ struct MatPen {
 //   a=t[i] b=t[i-1] c=t[j] d=t[j-1];  E[p] := D[t[p], t[p-1]] so D[a,b]=E[i], D[c,d]=E[j]
 template <class M, class T>
 __device__ Best sweep_two_opt_a2a(const int *t, int n, const M &D, double *E, bool fi, Best *red, T &team) {
-    for (int p = 1 + threadIdx.x; p <= n - 1; p += blockDim.x) E[p] = D(t[p], t[p - 1]);
-    __syncthreads();
     Best best;
     best.delta = 0.0; best.key = -1; best.pad = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if constexpr (T::kDeep) {
+        if (team.rows) {                                       // row cache (see struct Cluster); D is the plain global matrix
+            double *ra = team.rows + (size_t)warp * 2 * n, *rb = ra + n;
+            int i = 1 + team.first_row(warp);
+            // rows with few candidates (the last eighth) do not pay for copying two matrix rows
+            bool ahead = i <= n - 3 && (n - 2 - i) * 8 >= n;
+            if (ahead) {                                       // the first scan row's matrix rows and E travel together
+                stage_row_async(ra, D.p + (size_t)t[i] * D.ld, n, lane);
+                stage_row_async(rb, D.p + (size_t)t[i - 1] * D.ld, n, lane);
+            }
+            for (int p = 1 + threadIdx.x; p <= n - 1; p += blockDim.x) stage_elem_async(E + p, D.p + (size_t)t[p] * D.ld + t[p - 1]);
+            stage_commit();
+            stage_wait<0>();
+            __syncthreads();
+            for (; i <= n - 3; i += team.row_stride(nw)) {
+                const int a = t[i], b = t[i - 1];
+                const double Ei = E[i];
+                if ((n - 2 - i) * 8 >= n) {
+                    if (!ahead) {
+                        __syncwarp();                          // every lane is done with the previous rows
+                        stage_row_async(ra, D.p + (size_t)a * D.ld, n, lane);
+                        stage_row_async(rb, D.p + (size_t)b * D.ld, n, lane);
+                        stage_commit();
+                        stage_wait<0>();
+                        __syncwarp();
+                    }
+                    ahead = false;
+                    for (int j = i + 2 + lane; j <= n - 1; j += 32) {
+                        double x = __dadd_rn(ra[t[j]], rb[t[j - 1]]);
+                        x = __dsub_rn(x, Ei);
+                        x = __dsub_rn(x, E[j]);
+                        consider(best, x, (i << 16) | j, fi);
+                    }
+                } else {
+                    for (int j = i + 2 + lane; j <= n - 1; j += 32) {
+                        double x = __dadd_rn(D(a, t[j]), D(b, t[j - 1]));
+                        x = __dsub_rn(x, Ei);
+                        x = __dsub_rn(x, E[j]);
+                        consider(best, x, (i << 16) | j, fi);
+                    }
+                }
+            }
+            return team.reduce(best, fi, red);
+        }
+    }
+    for (int p = 1 + threadIdx.x; p <= n - 1; p += blockDim.x) E[p] = D(t[p], t[p - 1]);
+    __syncthreads();
     for (int i = 1 + team.first_row(warp); i <= n - 3; i += team.row_stride(nw)) {
         const int a = t[i], b = t[i - 1];
         const double Ei = E[i];
@@ -198,11 +283,47 @@ __device__ Best sweep_two_opt_a2a(const int *t, int n, const M &D, double *E, bo
 //   E[p] := D[t[p], t[p+1]] so D[a,b]=E[i-1], D[b,c]=E[i], D[d,e]=E[q]
 template <class M, class T>
 __device__ Best sweep_relocate_a2a(const int *t, int n, const M &D, double *E, bool fi, Best *red, T &team) {
-    for (int p = threadIdx.x; p <= n - 1; p += blockDim.x) E[p] = D(t[p], t[p + 1]);
-    __syncthreads();
     Best best;
     best.delta = 0.0; best.key = -1; best.pad = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if constexpr (T::kDeep) {
+        if (team.rows) {       // row cache: row b serves D[b][e] and, for a symmetric matrix, D[d][b]; double buffered over scan rows
+            double *rbuf = team.rows + (size_t)warp * 2 * n;
+            const bool sym = team.symmetric != 0;
+            const int stride = team.row_stride(nw);
+            int i = 1 + team.first_row(warp), cur = 0;
+            if (i <= n - 1) stage_row_async(rbuf, D.p + (size_t)t[i] * D.ld, n, lane);
+            for (int p = threadIdx.x; p <= n - 1; p += blockDim.x) stage_elem_async(E + p, D.p + (size_t)t[p] * D.ld + t[p + 1]);
+            stage_commit();
+            stage_wait<0>();
+            __syncthreads();
+            for (; i <= n - 1; i += stride) {
+                const int a = t[i - 1], b = t[i], c = t[i + 1];
+                if (i + stride <= n - 1) stage_row_async(rbuf + (cur ^ 1) * n, D.p + (size_t)t[i + stride] * D.ld, n, lane);
+                stage_commit();
+                double base = __dsub_rn(-E[i - 1], E[i]);
+                base = __dadd_rn(base, D(a, c));
+                stage_wait<1>();                               // this scan row's matrix row has landed (the next may be in flight)
+                __syncwarp();
+                const double *rb = rbuf + cur * n;
+                for (int j = 1 + lane; j <= n - 1; j += 32) {
+                    if (j == i || j == i - 1) continue;
+                    const int q = (i < j) ? j : j - 1;
+                    const int d = t[q], e = t[q + 1];
+                    double x = __dsub_rn(base, E[q]);
+                    x = __dadd_rn(x, sym ? rb[d] : D(d, b));
+                    x = __dadd_rn(x, rb[e]);
+                    consider(best, x, (i << 16) | j, fi);
+                }
+                __syncwarp();                                  // before this buffer is refilled two scan rows from now
+                cur ^= 1;
+            }
+            stage_wait<0>();
+            return team.reduce(best, fi, red);
+        }
+    }
+    for (int p = threadIdx.x; p <= n - 1; p += blockDim.x) E[p] = D(t[p], t[p + 1]);
+    __syncthreads();
     for (int i = 1 + team.first_row(warp); i <= n - 1; i += team.row_stride(nw)) {
         const int a = t[i - 1], b = t[i], c = t[i + 1];
         double base = __dsub_rn(-E[i - 1], E[i]);
@@ -429,7 +550,7 @@ template <bool CL> struct TeamOf { using type = Solo; };
 template <> struct TeamOf<true> { using type = Cluster; };
 
 template <bool CL>
-__device__ __forceinline__ typename TeamOf<CL>::type make_team(const Smem &s, int *inst0, int *inst_stride) {
+__device__ __forceinline__ typename TeamOf<CL>::type make_team(const Smem &s, int *inst0, int *inst_stride, double *rows = nullptr) {
     typename TeamOf<CL>::type team;
     if constexpr (CL) {
         cg::cluster_group cl = cg::this_cluster();
@@ -437,6 +558,8 @@ __device__ __forceinline__ typename TeamOf<CL>::type make_team(const Smem &s, in
         team.size = (int)cl.num_blocks();
         team.parity = 0;
         team.xch = s.xch;
+        team.rows = rows;
+        team.symmetric = 0;
         *inst0 = (int)blockIdx.x / team.size;
         *inst_stride = (int)gridDim.x / team.size;
     } else {
@@ -446,15 +569,29 @@ __device__ __forceinline__ typename TeamOf<CL>::type make_team(const Smem &s, in
     return team;
 }
 
+// D[a][b] == D[b][a] bit for bit?  Checked once per instance by the whole cluster (each member takes a share of the
+// pairs; the verdict travels through the winners' exchange: a candidate with key >= 0 means "found an asymmetric pair").
+__device__ void cluster_check_symmetric(const double *Dg, int n, Cluster &team, Best *red) {
+    if (!team.rows) return;
+    const long long *Db = reinterpret_cast<const long long *>(Dg);
+    int ok = 1;
+    for (int r = team.rank; r < n; r += team.size)
+        for (int c = r + 1 + threadIdx.x; c < n; c += blockDim.x) ok &= Db[(size_t)r * n + c] == Db[(size_t)c * n + r];
+    Best v;
+    v.delta = 0.0; v.key = ok ? -1 : 0; v.pad = 0;
+    team.symmetric = team.reduce(v, false, red).key < 0;
+}
+
 template <bool STAGE_D, bool CL>
 __device__ __forceinline__ void moves_body(int op, bool o2a, const double *Dg, int64_t d_stride, const int *tours,
                              const int *pos, int B, int n, int fi, double *out_delta, int *out_move,
-                             int *out_tours) {
+                             int *out_tours, int row_cache = 0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem s;
-    smem_layout(n, STAGE_D, false, false, &s, smem_raw);
+    const size_t used = smem_layout(n, STAGE_D, false, false, &s, smem_raw);
     int inst0, inst_stride;
-    auto team = make_team<CL>(s, &inst0, &inst_stride);
+    // (a single sweep does not pay for a symmetry check: relocate's column term stays a global gather)
+    auto team = make_team<CL>(s, &inst0, &inst_stride, row_cache ? reinterpret_cast<double *>(smem_raw + used) : nullptr);
     const bool writer = team.lead();
     for (int b = inst0; b < B; b += inst_stride) {
         const double *Db = Dg + (size_t)b * d_stride;
@@ -505,12 +642,12 @@ __device__ __forceinline__ void moves_body(int op, bool o2a, const double *Dg, i
 template <bool STAGE_D, bool CL>
 __device__ __forceinline__ void local_search_body(const double *Dg, int *tours, double *costs, int B, int n, int fi,
                                     double *events, int *n_events, int max_events, int *status,
-                                    long long *counters) {
+                                    long long *counters, int row_cache = 0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem s;
-    smem_layout(n, STAGE_D, false, false, &s, smem_raw);
+    const size_t used = smem_layout(n, STAGE_D, false, false, &s, smem_raw);
     int inst0, inst_stride;
-    auto team = make_team<CL>(s, &inst0, &inst_stride);
+    auto team = make_team<CL>(s, &inst0, &inst_stride, row_cache ? reinterpret_cast<double *>(smem_raw + used) : nullptr);
     const bool writer = team.lead();
     for (int b = inst0; b < B; b += inst_stride) {
         const double *Db = Dg + (size_t)b * n * n;
@@ -520,6 +657,7 @@ __device__ __forceinline__ void local_search_body(const double *Dg, int *tours, 
         else { D.p = Db; D.ld = n; }
         if (threadIdx.x == 0) s.slot[0] = costs[b];
         __syncthreads();
+        if constexpr (CL) cluster_check_symmetric(Db, n, team, s.red);
         EventLog log{(events && writer) ? events + (size_t)b * max_events : nullptr, max_events, 0};
         long long cnt[4] = {0, 0, 0, 0};
         local_search_dev(s, n, D, fi != 0, &s.slot[0], log, cnt, team);
@@ -549,6 +687,7 @@ struct GuideRef {
 
 struct GlsDev {
     gnngls_gls_args a;
+    int row_cache;   // cluster tier: per-warp row cache behind the regular shared-memory layout
 };
 
 constexpr int kStallCap = 1 << 16;   // safety cap on perturbation-loop trips per outer iteration
@@ -567,12 +706,12 @@ __device__ __forceinline__ void gls_body(const GlsDev &P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n;
     Smem s;
-    smem_layout(n, STAGED, true, STAGED, &s, smem_raw);
+    const size_t used = smem_layout(n, STAGED, true, STAGED, &s, smem_raw);
     const bool fi = a.first_improvement != 0;
     const size_t nn = (size_t)n * n;
     if (threadIdx.x == 0) s.ivars[0] = 0;
     int inst0, inst_stride;
-    auto team = make_team<CL>(s, &inst0, &inst_stride);
+    auto team = make_team<CL>(s, &inst0, &inst_stride, P.row_cache ? reinterpret_cast<double *>(smem_raw + used) : nullptr);
     const bool lead = team.lead();
 
     for (int b = inst0; b < a.B; b += inst_stride) {
@@ -602,6 +741,7 @@ __device__ __forceinline__ void gls_body(const GlsDev &P) {
         }
         if (a.resume) for (int p = threadIdx.x; p <= n; p += blockDim.x) s.best_tour[p] = a.best_tours[(size_t)b * (n + 1) + p];
         __syncthreads();
+        if constexpr (CL) cluster_check_symmetric(Db, n, team, s.red);
         double k;
         if (a.resume) k = a.k[b];
         else k = __ddiv_rn(__dmul_rn(0.1, s.slot[0]), (double)n);                // :137
@@ -740,8 +880,9 @@ __global__ void moves_kernel(int op, bool o2a, const double *Dg, int64_t d_strid
 }
 __global__ void __launch_bounds__(1024) moves_cluster_kernel(int op, bool o2a, const double *Dg, int64_t d_stride,
                                                              const int *tours, const int *pos, int B, int n, int fi,
-                                                             double *out_delta, int *out_move, int *out_tours) {
-    moves_body<false, true>(op, o2a, Dg, d_stride, tours, pos, B, n, fi, out_delta, out_move, out_tours);
+                                                             double *out_delta, int *out_move, int *out_tours,
+                                                             int row_cache) {
+    moves_body<false, true>(op, o2a, Dg, d_stride, tours, pos, B, n, fi, out_delta, out_move, out_tours, row_cache);
 }
 template <bool STAGE_D>
 __global__ void local_search_kernel(const double *Dg, int *tours, double *costs, int B, int n, int fi, double *events,
@@ -750,8 +891,9 @@ __global__ void local_search_kernel(const double *Dg, int *tours, double *costs,
 }
 __global__ void __launch_bounds__(1024) local_search_cluster_kernel(const double *Dg, int *tours, double *costs, int B,
                                                                     int n, int fi, double *events, int *n_events,
-                                                                    int max_events, int *status, long long *counters) {
-    local_search_body<false, true>(Dg, tours, costs, B, n, fi, events, n_events, max_events, status, counters);
+                                                                    int max_events, int *status, long long *counters,
+                                                                    int row_cache) {
+    local_search_body<false, true>(Dg, tours, costs, B, n, fi, events, n_events, max_events, status, counters, row_cache);
 }
 template <bool STAGED>
 __global__ void gls_kernel(const GlsDev P) { gls_body<STAGED, false>(P); }
@@ -974,39 +1116,72 @@ int max_active_clusters(const void *kernel, int csize, int threads, size_t smem)
     return mc;
 }
 
-// Launches `kernel` with clusters of CTAs (grid = clusters x size), as many clusters as instances but no more than can be
-// co-resident (the kernels loop over instances).  `limit` comes from cluster_limit_for().  Among the cluster sizes up to the
-// limit and CTA sizes (the one-CTA tier's, or 512 threads so that two CTAs share an SM) the launch takes the combination
-// with the smallest (rounds of co-resident clusters) / (threads per instance).
-template <typename... KArgs, typename... Args>
-int launch_clustered(void (*kernel)(KArgs...), int limit, int B, int n, size_t smem, cudaStream_t st,
-                     const char *what, Args... args) {
-    GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    if (smem > 48 * 1024)
-        GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const void *kp = reinterpret_cast<const void *>(kernel);
-    const int t_full = pick_threads(n), t_half = cluster_threads(n);
-    int best_c = 0, best_mc = 0, best_t = 0;
+// Shape of a cluster-tier launch.  `limit` comes from cluster_limit_for().  Among the cluster sizes up to the limit and the CTA
+// sizes on offer the plan takes the combination with the smallest (rounds of co-resident clusters) / (threads per instance).
+// With the row cache (n >= kRowCacheMinN, or GNNGLS_ROWCACHE=1; =0 disables) a CTA has as many warps as 16 n bytes of shared memory
+// each allow; without it the CTA sizes are the one-CTA tier's and 512 threads (two CTAs per SM).
+constexpr int kRowCacheMinN = 192;
+
+struct ClusterPlan {
+    int csize = 0, threads = 0, clusters = 0, row_cache = 0;
+    size_t smem = 0;
+};
+
+int plan_cluster(const void *kernel, int limit, int B, int n, size_t base_smem, const char *what, ClusterPlan *plan) {
+    int want_rows = n >= kRowCacheMinN;
+    if (const char *e = getenv("GNNGLS_ROWCACHE")) want_rows = atoi(e) != 0;
+    const size_t row_bytes = 2 * sizeof(double) * (size_t)n;          // per warp
+    const size_t room = (size_t)gnngls::device_max_optin_smem() - 1024;
+    int options[2] = {0, 0};
+    if (want_rows && base_smem + 4 * row_bytes <= room) {
+        int warps = (int)((room - base_smem) / row_bytes);
+        if (warps > pick_threads(n) / 32) warps = pick_threads(n) / 32;
+        options[0] = 32 * warps;
+        options[1] = warps >= 8 ? 32 * (warps / 2) : 0;
+    } else {
+        want_rows = 0;
+        options[0] = pick_threads(n);
+        options[1] = cluster_threads(n) < options[0] ? cluster_threads(n) : 0;
+    }
     double best_score = 0.0;
-    for (int threads = t_full; threads >= t_half; threads = (threads == t_half ? 0 : t_half)) {
+    for (int o = 0; o < 2; ++o) {
+        const int threads = options[o];
+        if (!threads) continue;
+        const size_t smem = base_smem + (want_rows ? (size_t)(threads / 32) * row_bytes : 0);
         for (int c = limit < 0 ? -limit : limit; c >= 2; c /= 2) {
-            const int mc = max_active_clusters(kp, c, threads, smem);
+            const int mc = max_active_clusters(kernel, c, threads, smem);
             if (mc < 1) continue;
             const int rounds = (B + mc - 1) / mc;
             const double score = (double)rounds / ((double)c * threads);
             // ties go to the smaller CTA: two of them share an SM's L1 and registers more evenly than one large one
-            if (!best_c || score <= best_score) { best_c = c; best_mc = mc; best_t = threads; best_score = score; }
+            if (!plan->csize || score <= best_score) {
+                plan->csize = c; plan->threads = threads; plan->clusters = B < mc ? B : mc; plan->smem = smem;
+                plan->row_cache = want_rows;
+                best_score = score;
+            }
             if (limit < 0) break;                      // forced: that size, or the next smaller one that can be placed
         }
     }
-    GNNGLS_REQUIRE(best_c >= 2, GNNGLS_ERR_CUDA, "launch of %s failed: no cluster size could be placed", what);
+    GNNGLS_REQUIRE(plan->csize >= 2, GNNGLS_ERR_CUDA, "launch of %s failed: no cluster size could be placed", what);
+    return GNNGLS_OK;
+}
+
+template <typename K>
+int prepare_cluster_kernel(K kernel) {
+    GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gnngls::device_max_optin_smem()));
+    return GNNGLS_OK;
+}
+
+template <typename... KArgs, typename... Args>
+int launch_planned(void (*kernel)(KArgs...), const ClusterPlan &plan, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = best_c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = plan.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(best_t); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cfg.gridDim = dim3((B < best_mc ? B : best_mc) * best_c);
+    cfg.blockDim = dim3(plan.threads); cfg.dynamicSmemBytes = plan.smem; cfg.stream = st;
+    cfg.gridDim = dim3(plan.clusters * plan.csize);
     GNNGLS_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
     return GNNGLS_OK;
 }
@@ -1030,9 +1205,13 @@ int launch_moves(int op, bool o2a, const double *D, int64_t stride, const int *t
     // One sweep per instance does not amortise staging an n x n fp64 matrix into shared memory (measured: 6x slower at
     // n=100); stage only a matrix shared by the whole batch.  local_search / GLS, which sweep many times, always stage.
     const int csize = o2a ? 1 : cluster_limit_for(B, n);
-    if (csize != 1)
-        return launch_clustered(moves_cluster_kernel, csize, B, n, plain, st, "moves_cluster_kernel", op, o2a,
-                                D, stride, tours, pos, B, n, fi, out_delta, out_move, out_tours);
+    if (csize != 1) {
+        ClusterPlan plan;
+        if (int rc = prepare_cluster_kernel(moves_cluster_kernel)) return rc;
+        if (int rc = plan_cluster(reinterpret_cast<const void *>(moves_cluster_kernel), csize, B, n, plain, "moves_cluster_kernel", &plan)) return rc;
+        return launch_planned(moves_cluster_kernel, plan, st, op, o2a, D, stride, tours, pos, B, n, fi, out_delta, out_move,
+                              out_tours, plan.row_cache);
+    }
     if (stride == 0 && staged <= limit) {
         if (int rc = ensure_smem(moves_kernel<true>, staged)) return rc;
         moves_kernel<true><<<grid_for(B), threads, staged, st>>>(op, o2a, D, stride, tours, pos, B, n, fi,
@@ -1073,10 +1252,14 @@ extern "C" int gnngls_local_search_batch(const double *D, int32_t *tours, double
     const size_t staged = smem_layout(n, true, false, false, nullptr, nullptr);
     const size_t plain = smem_layout(n, false, false, false, nullptr, nullptr);
     const int csize = cluster_limit_for(B, n);
-    if (csize != 1)
-        return launch_clustered(local_search_cluster_kernel, csize, B, n, plain, st,
-                                "local_search_cluster_kernel", D, tours, costs, B, n, first_improvement, events, n_events,
-                                max_events, status, reinterpret_cast<long long *>(counters));
+    if (csize != 1) {
+        ClusterPlan plan;
+        if (int rc = prepare_cluster_kernel(local_search_cluster_kernel)) return rc;
+        if (int rc = plan_cluster(reinterpret_cast<const void *>(local_search_cluster_kernel), csize, B, n, plain,
+                                  "local_search_cluster_kernel", &plan)) return rc;
+        return launch_planned(local_search_cluster_kernel, plan, st, D, tours, costs, B, n, first_improvement, events, n_events,
+                              max_events, status, reinterpret_cast<long long *>(counters), plan.row_cache);
+    }
     if (staged <= (size_t)gnngls::device_max_optin_smem()) {
         if (int rc = ensure_smem(local_search_kernel<true>, staged)) return rc;
         local_search_kernel<true><<<grid_for(B), threads, staged, st>>>(
@@ -1111,6 +1294,7 @@ extern "C" int gnngls_gls_batch(const gnngls_gls_args *args, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GlsDev P;
     P.a = a;
+    P.row_cache = 0;
     const int threads = pick_threads(a.n);
     const size_t staged = smem_layout(a.n, true, true, true, nullptr, nullptr);
     const size_t plain = smem_layout(a.n, false, true, false, nullptr, nullptr);
@@ -1123,9 +1307,14 @@ extern "C" int gnngls_gls_batch(const gnngls_gls_args *args, void *stream) {
     const bool fits = staged <= (size_t)gnngls::device_max_optin_smem();
     const bool use_global = a.penalties && (tier == 2 || (tier == 0 && a.n >= 64)) ;
     const int csize = a.penalties ? cluster_limit_for(a.B, a.n) : 1;   // the cluster tier keeps the penalties in global memory
-    if (csize != 1)
-        return launch_clustered(gls_cluster_kernel, csize, a.B, a.n, plain, st,
-                                "gls_cluster_kernel", P);
+    if (csize != 1) {
+        ClusterPlan plan;
+        if (int rc = prepare_cluster_kernel(gls_cluster_kernel)) return rc;
+        if (int rc = plan_cluster(reinterpret_cast<const void *>(gls_cluster_kernel), csize, a.B, a.n, plain, "gls_cluster_kernel", &plan))
+            return rc;
+        P.row_cache = plan.row_cache;
+        return launch_planned(gls_cluster_kernel, plan, st, P);
+    }
     if (fits && !use_global) {
         if (int rc = ensure_smem(gls_kernel<true>, staged)) return rc;
         gls_kernel<true><<<grid_for(a.B), threads, staged, st>>>(P);
