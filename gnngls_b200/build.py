@@ -22,7 +22,7 @@ COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-I', INCLUDE
 # per-translation-unit extra flags; the search/glue units must never contract a*b+c into an FMA
 SOURCES = {
     'common.cu': [],
-    'search.cu': ['-fmad=false'],
+    'search.cu': ['-fmad=false'] + (['-DGLS_STAMPS'] if os.environ.get('GNNGLS_GLS_STAMPS') else []),   # phase timers (tools/gls_stamps.py)
     'glue.cu': ['-fmad=false'],
     'gat.cu': [],
     'gat_kn.cu': [],

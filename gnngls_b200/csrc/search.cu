@@ -23,6 +23,27 @@ namespace {
 
 using gnngls::set_error;
 
+// Phase timing of the cluster tier (debug builds only: GNNGLS_GLS_STAMPS=1 python -m gnngls_b200.build --force): thread 0 of every
+// CTA accumulates clock64() differences per phase of a sweep; read back with gnngls_debug_gls_stamps() (tools/gls_stamps.py).
+#ifdef GLS_STAMPS
+__device__ unsigned long long g_gls_stamps[16 * 8];
+__device__ __forceinline__ long long *gls_stamp_buf() {
+    static __shared__ long long buf[9];      // [8]: last clock
+    return buf;
+}
+#define GLS_STAMP(slot)                                              \
+    do {                                                             \
+        if (threadIdx.x == 0) {                                      \
+            long long *sb__ = gls_stamp_buf();                       \
+            const long long now__ = clock64();                       \
+            sb__[slot] += now__ - sb__[8];                           \
+            sb__[8] = now__;                                         \
+        }                                                            \
+    } while (0)
+#else
+#define GLS_STAMP(slot) do { } while (0)
+#endif
+
 // ----------------------------------------------------------------------------------------------
 // candidate bookkeeping
 // ----------------------------------------------------------------------------------------------
@@ -39,52 +60,79 @@ __device__ __forceinline__ bool close_to_zero(double d) {
     return ad <= __dadd_rn(1e-8, __dmul_rn(1e-5, ad));
 }
 
-// operators.py:41-46: accept iff delta < best_delta (best starts at 0) and not isclose(0, delta)
+// operators.py:41-46: accept iff delta < best_delta (best starts at 0) and not isclose(0, delta).
+// Every thread meets its candidates in increasing scan rank (rows ascending, j ascending), so inside a thread an equal delta
+// never replaces the incumbent and, with first_improvement, only the first acceptable candidate is ever taken: one fp64
+// compare per candidate, the isclose test only for candidates that would otherwise win.
 __device__ __forceinline__ void consider(Best &b, double delta, int key, bool fi) {
-    if (delta < 0.0 && !close_to_zero(delta)) {
-        const bool take = (b.key < 0) || (fi ? (key < b.key)
-                                             : (delta < b.delta || (delta == b.delta && key < b.key)));
-        if (take) { b.delta = delta; b.key = key; }
+    if (delta < b.delta) {                                  // b.delta is 0 until a candidate is accepted, < 0 afterwards
+        if ((!fi || b.key < 0) && !close_to_zero(delta)) { b.delta = delta; b.key = key; }
     }
 }
 
-__device__ __forceinline__ Best pick(Best a, Best b, bool fi) {
+// general order on (value, rank): used for the utility arg-max, whose values have any sign
+__device__ __forceinline__ Best pick_any(Best a, Best b) {
     if (b.key < 0) return a;
     if (a.key < 0) return b;
-    if (fi) return (a.key < b.key) ? a : b;
     if (a.delta < b.delta) return a;
     if (b.delta < a.delta) return b;
     return (a.key < b.key) ? a : b;
 }
 
+// The winner of two move candidates.  An accepted candidate has delta < 0 and key >= 0; "none" is (+0.0, -1).  For non-positive
+// doubles "more negative" is "larger bit pattern", and -1 is the largest unsigned key, so the reference's order -- smaller delta,
+// then smaller scan rank; with first_improvement the smaller scan rank alone -- is two integer compares, no branches.
+__device__ __forceinline__ Best pick(Best a, Best b, bool fi) {
+    const unsigned long long ua = (unsigned long long)__double_as_longlong(a.delta), ub = (unsigned long long)__double_as_longlong(b.delta);
+    const bool kb = (unsigned)b.key < (unsigned)a.key;
+    const bool tb = fi ? kb : (ub > ua || (ub == ua && kb));
+    Best r;
+    r.delta = tb ? b.delta : a.delta; r.key = tb ? b.key : a.key; r.pad = 0;
+    return r;
+}
+
+template <bool ANY>
 __device__ __forceinline__ Best warp_reduce_best(Best v, bool fi) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         Best o;
         o.delta = __shfl_xor_sync(0xffffffffu, v.delta, off);
         o.key = __shfl_xor_sync(0xffffffffu, v.key, off);
-        v = pick(v, o, fi);
+        v = ANY ? pick_any(v, o) : pick(v, o, fi);
     }
     return v;
 }
 
-// result is returned to every thread; `red` is shared scratch of 33 entries
+// result is returned to every thread; `red` is shared scratch of 32 entries.  Every warp combines the warps' winners itself,
+// so there are two block barriers: partial winners visible / scratch free again.
+template <bool ANY = false>
 __device__ Best block_reduce_best(Best v, bool fi, Best *red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    v = warp_reduce_best(v, fi);
+    v = warp_reduce_best<ANY>(v, fi);
     if (lane == 0) red[warp] = v;
     __syncthreads();
-    if (warp == 0) {
-        Best w;
-        w.delta = 0.0; w.key = -1; w.pad = 0;
-        if (lane < nw) w = red[lane];
-        w = warp_reduce_best(w, fi);
-        if (lane == 0) red[32] = w;
-    }
-    __syncthreads();
-    Best r = red[32];
+    Best w;
+    w.delta = 0.0; w.key = -1; w.pad = 0;
+    if (lane < nw) w = red[lane];
+    w = warp_reduce_best<ANY>(w, fi);
     __syncthreads();   // red may be reused immediately by the caller
-    return r;
+    return w;
+}
+
+// the same with one barrier: the scratch (2 x 32 entries) is double buffered by the caller's reduction count -- a warp can be at
+// most one barrier ahead of the slowest, so the half it overwrites was read two barriers ago
+__device__ Best block_reduce_best_db(Best v, bool fi, Best *red2, int &parity) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_reduce_best<false>(v, fi);
+    Best *r = red2 + parity * 32;
+    if (lane == 0) r[warp] = v;
+    __syncthreads();
+    Best w;
+    w.delta = 0.0; w.key = -1; w.pad = 0;
+    if (lane < nw) w = r[lane];
+    w = warp_reduce_best<false>(w, fi);
+    parity ^= 1;
+    return w;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -99,7 +147,8 @@ constexpr int kMaxCluster = 16;
 struct Solo {
     __device__ __forceinline__ int first_row(int warp) const { return warp; }
     __device__ __forceinline__ int row_stride(int nw) const { return nw; }
-    __device__ __forceinline__ Best reduce(Best v, bool fi, Best *red) { return block_reduce_best(v, fi, red); }
+    int rp = 0;                                               // parity of the double-buffered block reduction
+    __device__ __forceinline__ Best reduce(Best v, bool fi, Best *red) { return block_reduce_best_db(v, fi, red + 32, rp); }
     __device__ __forceinline__ bool lead() const { return true; }
     static constexpr bool kDeep = false;
 };
@@ -110,7 +159,7 @@ struct Solo {
 // buffered by the parity of the sweep count: a member can only be one barrier ahead, so the slots it overwrites were
 // read two barriers ago.
 struct Cluster {
-    int rank, size, parity;
+    int rank, size, parity, rp;
     Best *xch;      // [2][kMaxCluster] in this CTA's shared memory
     // Row cache (large n): a lane's gather D[a][t[j]] touches a different 128-byte line for almost every lane, and the L1 tag
     // stage serves about one line per cycle -- at n = 500 that, not latency or bandwidth, is what a sweep costs (ncu: 26 sectors
@@ -126,11 +175,14 @@ struct Cluster {
     // worth of gathers in flight per lane
     static constexpr bool kDeep = true;
     __device__ Best reduce(Best v, bool fi, Best *red) {
-        v = block_reduce_best(v, fi, red);
+        GLS_STAMP(1);                                          // rows
+        v = block_reduce_best_db(v, fi, red + 32, rp);
+        GLS_STAMP(2);                                          // reduction inside the CTA (waits for its slowest warp)
         cg::cluster_group cl = cg::this_cluster();
         Best *mine = xch + parity * kMaxCluster;
         if ((int)threadIdx.x < size) *cl.map_shared_rank(mine + rank, threadIdx.x) = v;
         cl.sync();
+        GLS_STAMP(3);                                          // exchange + cluster barrier (waits for the slowest member)
         Best w;                                                // every warp combines the (at most 16) winners itself
         w.delta = 0.0; w.key = -1; w.pad = 0;
         const int lane = threadIdx.x & 31;
@@ -145,6 +197,7 @@ struct Cluster {
         w.delta = __shfl_sync(0xffffffffu, w.delta, 0);
         w.key = __shfl_sync(0xffffffffu, w.key, 0);
         parity ^= 1;
+        GLS_STAMP(4);                                          // combine
         return w;
     }
 };
@@ -216,6 +269,7 @@ __device__ Best sweep_two_opt_a2a(const int *t, int n, const M &D, double *E, bo
             stage_commit();
             stage_wait<0>();
             __syncthreads();
+            GLS_STAMP(0);                                      // E (+ first rows) landed
             for (; i <= n - 3; i += team.row_stride(nw)) {
                 const int a = t[i], b = t[i - 1];
                 const double Ei = E[i];
@@ -229,7 +283,17 @@ __device__ Best sweep_two_opt_a2a(const int *t, int n, const M &D, double *E, bo
                         __syncwarp();
                     }
                     ahead = false;
-                    for (int j = i + 2 + lane; j <= n - 1; j += 32) {
+                    int j = i + 2 + lane;
+                    for (; j + 96 <= n - 1; j += 128) {        // four candidates per lane in flight (few warps: latency, not issue, bound)
+                        double x[4], y[4], e[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { x[u] = ra[t[j + 32 * u]]; y[u] = rb[t[j + 32 * u - 1]]; e[u] = E[j + 32 * u]; }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) x[u] = __dsub_rn(__dsub_rn(__dadd_rn(x[u], y[u]), Ei), e[u]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) consider(best, x[u], (i << 16) | (j + 32 * u), fi);
+                    }
+                    for (; j <= n - 1; j += 32) {
                         double x = __dadd_rn(ra[t[j]], rb[t[j - 1]]);
                         x = __dsub_rn(x, Ei);
                         x = __dsub_rn(x, E[j]);
@@ -297,6 +361,7 @@ __device__ Best sweep_relocate_a2a(const int *t, int n, const M &D, double *E, b
             stage_commit();
             stage_wait<0>();
             __syncthreads();
+            GLS_STAMP(0);                                      // E (+ first rows) landed
             for (; i <= n - 1; i += stride) {
                 const int a = t[i - 1], b = t[i], c = t[i + 1];
                 if (i + stride <= n - 1) stage_row_async(rbuf + (cur ^ 1) * n, D.p + (size_t)t[i + stride] * D.ld, n, lane);
@@ -306,7 +371,25 @@ __device__ Best sweep_relocate_a2a(const int *t, int n, const M &D, double *E, b
                 stage_wait<1>();                               // this scan row's matrix row has landed (the next may be in flight)
                 __syncwarp();
                 const double *rb = rbuf + cur * n;
-                for (int j = 1 + lane; j <= n - 1; j += 32) {
+                int j = 1 + lane;
+                if (sym) {
+                    for (; j + 96 <= n - 1; j += 128) {        // four candidates per lane in flight
+                        double x[4], y[4], e[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int ju = j + 32 * u, q = (i < ju) ? ju : ju - 1;   // ju in {i, i-1}: valid indices, dropped below
+                            x[u] = rb[t[q]]; y[u] = rb[t[q + 1]]; e[u] = E[q];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) x[u] = __dadd_rn(__dadd_rn(__dsub_rn(base, e[u]), x[u]), y[u]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int ju = j + 32 * u;
+                            if (ju != i && ju != i - 1) consider(best, x[u], (i << 16) | ju, fi);
+                        }
+                    }
+                }
+                for (; j <= n - 1; j += 32) {
                     if (j == i || j == i - 1) continue;
                     const int q = (i < j) ? j : j - 1;
                     const int d = t[q], e = t[q + 1];
@@ -457,7 +540,7 @@ struct Smem {
     double *D;       // n*ld (only when staged)
     double *E;       // n+1 per-position edge terms
     double *slot;    // 4 doubles of block-shared scalars
-    Best *red;       // 33
+    Best *red;       // 32 (two-barrier reductions) + 2 x 32 (one-barrier, double buffered)
     Best *xch;       // 2 x kMaxCluster winners exchanged between the CTAs of a cluster
     int *tour;       // n+1
     int *tmp;        // n+1
@@ -474,7 +557,7 @@ __host__ __device__ inline size_t smem_layout(int n, bool stage_d, bool gls, boo
     size_t oD = stage_d ? take(sizeof(double) * (size_t)n * ld_for(n)) : 0;
     size_t oE = take(sizeof(double) * (n + 1));
     size_t oS = take(sizeof(double) * 4);
-    size_t oR = take(sizeof(Best) * 33);
+    size_t oR = take(sizeof(Best) * 96);
     size_t oX = take(sizeof(Best) * 2 * kMaxCluster);
     size_t oT = take(sizeof(int) * (n + 1));
     size_t oM = take(sizeof(int) * (n + 1));
@@ -536,6 +619,7 @@ __device__ void local_search_dev(const Smem &s, int n, const M &D, bool fi, doub
                     cnt[3] += 1;
                 }
             }
+            GLS_STAMP(5);                                      // move applied, cost and log updated
         }
     }
     __syncthreads();
@@ -557,6 +641,7 @@ __device__ __forceinline__ typename TeamOf<CL>::type make_team(const Smem &s, in
         team.rank = (int)cl.block_rank();
         team.size = (int)cl.num_blocks();
         team.parity = 0;
+        team.rp = 0;
         team.xch = s.xch;
         team.rows = rows;
         team.symmetric = 0;
@@ -658,9 +743,15 @@ __device__ __forceinline__ void local_search_body(const double *Dg, int *tours, 
         if (threadIdx.x == 0) s.slot[0] = costs[b];
         __syncthreads();
         if constexpr (CL) cluster_check_symmetric(Db, n, team, s.red);
+#ifdef GLS_STAMPS
+        if (threadIdx.x == 0) { long long *sb = gls_stamp_buf(); for (int q = 0; q < 8; ++q) sb[q] = 0; sb[8] = clock64(); }
+#endif
         EventLog log{(events && writer) ? events + (size_t)b * max_events : nullptr, max_events, 0};
         long long cnt[4] = {0, 0, 0, 0};
         local_search_dev(s, n, D, fi != 0, &s.slot[0], log, cnt, team);
+#ifdef GLS_STAMPS
+        if constexpr (CL) if (threadIdx.x == 0 && b == inst0) for (int q = 0; q < 8; ++q) g_gls_stamps[(blockIdx.x & 15) * 8 + q] = gls_stamp_buf()[q];
+#endif
         // every member has read the instance's tour before the first barrier of the search; member 0 writes it back
         if (writer) for (int p = threadIdx.x; p <= n; p += blockDim.x) tours[(size_t)b * (n + 1) + p] = s.tour[p];
         if (threadIdx.x == 0 && writer) {
@@ -780,7 +871,7 @@ __device__ __forceinline__ void gls_body(const GlsDev &P) {
                     const double neg = (util != util) ? INFINITY : -util;       // NaN guide: never the arg-max
                     if (u.key < 0 || neg < u.delta) { u.delta = neg; u.key = p; }
                 }
-                u = block_reduce_best(u, false, s.red);
+                u = block_reduce_best<true>(u, false, s.red);
                 const int pe = u.key;
                 const int eu = s.tour[pe], ev = s.tour[pe + 1];
                 __syncthreads();
@@ -1169,7 +1260,10 @@ int plan_cluster(const void *kernel, int limit, int B, int n, size_t base_smem, 
 template <typename K>
 int prepare_cluster_kernel(K kernel) {
     GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gnngls::device_max_optin_smem()));
+    cudaFuncAttributes fa;
+    GNNGLS_CUDA_OK(cudaFuncGetAttributes(&fa, kernel));
+    GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        gnngls::device_max_optin_smem() - (int)fa.sharedSizeBytes));
     return GNNGLS_OK;
 }
 
@@ -1366,4 +1460,16 @@ extern "C" int gnngls_tour_cost_batch(const double *D, const int32_t *tours, int
                                                                                               out_costs);
     GNNGLS_LAUNCH_OK("tour_cost_kernel");
     return GNNGLS_OK;
+}
+
+// debug: per-(cluster member, phase) cycle totals of the last cluster local_search launch (error unless built with -DGLS_STAMPS)
+extern "C" int gnngls_debug_gls_stamps(unsigned long long *out, int count) {
+#ifdef GLS_STAMPS
+    if (count > 16 * 8) count = 16 * 8;
+    GNNGLS_CUDA_OK(cudaMemcpyFromSymbol(out, g_gls_stamps, sizeof(unsigned long long) * count));
+    return GNNGLS_OK;
+#else
+    (void)out; (void)count;
+    return GNNGLS_ERR_UNSUPPORTED;
+#endif
 }
