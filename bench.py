@@ -325,14 +325,17 @@ def main():
             if str(t.get('kernel', '')).startswith('gat_kn_tc_kernel') and t.get('n') == n:
                 traffic = t['dram_bytes_per_instance_layer'] * per_call_instances
                 traffic_src = t.get('source')
-        roof = {'kernel': 'gat_kn_tc_kernel (K_n edge-softmax/aggregate + skip + BN1 on tcgen05)',
+        tc_kernel = n <= 128        # csrc/gat_kn.cu: larger stars run the exact sorted-prefix kernel
+        roof = {'kernel': 'gat_kn_tc_kernel (K_n edge-softmax/aggregate + skip + BN1 on tcgen05)' if tc_kernel else
+                          'gat_kn_scan_kernel (K_n edge-softmax/aggregate + skip + BN1, exact sorted-prefix sums, n > 128)',
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': N_nodes * node_bytes * per_call_instances,
                 'avg_launch_ms': gat_ms / gat_calls, 'launches_timed': gat_calls,
                 'logical_gather_gbs': (E * 544 + N_nodes * 544) * inst_layers / (gat_ms / 1e3) / 1e9,
-                'limiter': 'latency / instruction issue, not HBM (profiles/r2_kn_tc.md): the HBM fraction says how far the '
-                           'kernel is from the only roofline that bounds its compulsory traffic'}
+                'limiter': ('latency / instruction issue, not HBM (profiles/r2_kn_tc.md)' if tc_kernel else
+                            'sort + prefix-sum latency per star, not HBM (profiles/r2_kernels_n500.md)') +
+                           ': the HBM fraction says how far the kernel is from the only roofline that bounds its compulsory traffic'}
     # the other model kernels against the same HBM peak (compulsory bytes per node and layer / measured stage time)
     other = {}
     for name, nbytes, nlaunch in (('fc', 256 + 256 + 64, 8), ('ff', 512 + 512 + 256, 8)):

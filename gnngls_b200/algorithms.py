@@ -40,7 +40,8 @@ def guided_local_search_batch(D, guides, init_tours, init_costs, n_iters, pertur
     """guides: [B,n_guides,n,n] fp64 or [B,n_guides,N] fp32.  Returns (best_tours, best_costs, info);
     info additionally carries the resumable ``state``."""
     kind = _ops.GUIDE_MATRIX_F64 if guides.dtype == torch.float64 else _ops.GUIDE_EDGEVEC_F32
-    state = _ops.GlsState(D, guides, kind, init_tours, init_costs, keep_penalties=keep_penalties)
+    # a penalties buffer lets the kernel use its L2-resident and cluster tiers (csrc/search.cu), as pipeline.RegretGLS.solve does
+    state = _ops.GlsState(D, guides, kind, init_tours, init_costs, keep_penalties=keep_penalties or D.shape[-1] >= 64)
     info = _ops.gls_run(state, n_iters, perturbation_moves, first_improvement, max_events, want_counters=True)
     info['state'] = state
     return state.best_tours, state.best_costs, info

@@ -647,6 +647,8 @@ __device__ __forceinline__ typename TeamOf<CL>::type make_team(const Smem &s, in
         team.symmetric = 0;
         *inst0 = (int)blockIdx.x / team.size;
         *inst_stride = (int)gridDim.x / team.size;
+        cl.sync();             // distributed shared memory of a member may only be touched once that member has started
+                               // (compute-sanitizer: "located in a block that might not have entered yet")
     } else {
         *inst0 = (int)blockIdx.x;
         *inst_stride = (int)gridDim.x;
@@ -1218,42 +1220,46 @@ struct ClusterPlan {
     size_t smem = 0;
 };
 
-int plan_cluster(const void *kernel, int limit, int B, int n, size_t base_smem, const char *what, ClusterPlan *plan) {
-    int want_rows = n >= kRowCacheMinN;
-    if (const char *e = getenv("GNNGLS_ROWCACHE")) want_rows = atoi(e) != 0;
+int plan_cluster(const void *kernel, int limit, int B, int n, size_t base_smem, const char *what, ClusterPlan *plan,
+                 bool rows_allowed = true) {
+    int want_rows = rows_allowed && n >= kRowCacheMinN;
+    if (const char *e = getenv("GNNGLS_ROWCACHE")) want_rows = rows_allowed && atoi(e) != 0;
     const size_t row_bytes = 2 * sizeof(double) * (size_t)n;          // per warp
     const size_t room = (size_t)gnngls::device_max_optin_smem() - 1024;
-    int options[2] = {0, 0};
+    struct Option { int threads, rows; } options[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    options[0].threads = pick_threads(n);
+    options[1].threads = cluster_threads(n) < options[0].threads ? cluster_threads(n) : 0;
     if (want_rows && base_smem + 4 * row_bytes <= room) {
         int warps = (int)((room - base_smem) / row_bytes);
         if (warps > pick_threads(n) / 32) warps = pick_threads(n) / 32;
-        options[0] = 32 * warps;
-        options[1] = warps >= 8 ? 32 * (warps / 2) : 0;
-    } else {
-        want_rows = 0;
-        options[0] = pick_threads(n);
-        options[1] = cluster_threads(n) < options[0] ? cluster_threads(n) : 0;
+        options[2] = Option{32 * warps, 1};
+        options[3] = Option{warps >= 8 ? 32 * (warps / 2) : 0, 1};
+        if (getenv("GNNGLS_ROWCACHE")) options[0].threads = options[1].threads = 0;     // forced on: only the row-cache shapes
     }
     double best_score = 0.0;
-    for (int o = 0; o < 2; ++o) {
-        const int threads = options[o];
-        if (!threads) continue;
-        const size_t smem = base_smem + (want_rows ? (size_t)(threads / 32) * row_bytes : 0);
+    for (const Option &o : options) {
+        if (!o.threads) continue;
+        const size_t smem = base_smem + (o.rows ? (size_t)(o.threads / 32) * row_bytes : 0);
         for (int c = limit < 0 ? -limit : limit; c >= 2; c /= 2) {
-            const int mc = max_active_clusters(kernel, c, threads, smem);
+            const int mc = max_active_clusters(kernel, c, o.threads, smem);
             if (mc < 1) continue;
             const int rounds = (B + mc - 1) / mc;
-            const double score = (double)rounds / ((double)c * threads);
+            // a thread with the row cache gets ~1.35 x the work done (n = 500: 864 threads 7.0 ms, 1024 threads without 8.1 ms)
+            const double score = (double)rounds / ((double)c * o.threads * (o.rows ? 1.35 : 1.0));
             // ties go to the smaller CTA: two of them share an SM's L1 and registers more evenly than one large one
             if (!plan->csize || score <= best_score) {
-                plan->csize = c; plan->threads = threads; plan->clusters = B < mc ? B : mc; plan->smem = smem;
-                plan->row_cache = want_rows;
+                plan->csize = c; plan->threads = o.threads; plan->clusters = B < mc ? B : mc; plan->smem = smem;
+                plan->row_cache = o.rows;
                 best_score = score;
             }
             if (limit < 0) break;                      // forced: that size, or the next smaller one that can be placed
         }
     }
     GNNGLS_REQUIRE(plan->csize >= 2, GNNGLS_ERR_CUDA, "launch of %s failed: no cluster size could be placed", what);
+    // A cluster must bring clearly more threads to an instance than the one-CTA tier would (which runs every eligible batch in one
+    // round): with the row cache's small CTAs and a batch that needs two rounds of clusters it does not (n = 1000 x 64: 2 x 416
+    // against 1024 threads, measured slower) -- csize = 1 tells the caller to launch the one-CTA tier.
+    if (limit > 0 && 2LL * plan->csize * plan->threads * plan->clusters < 3LL * pick_threads(n) * B) plan->csize = 1;
     return GNNGLS_OK;
 }
 
@@ -1302,9 +1308,12 @@ int launch_moves(int op, bool o2a, const double *D, int64_t stride, const int *t
     if (csize != 1) {
         ClusterPlan plan;
         if (int rc = prepare_cluster_kernel(moves_cluster_kernel)) return rc;
-        if (int rc = plan_cluster(reinterpret_cast<const void *>(moves_cluster_kernel), csize, B, n, plain, "moves_cluster_kernel", &plan)) return rc;
-        return launch_planned(moves_cluster_kernel, plan, st, op, o2a, D, stride, tours, pos, B, n, fi, out_delta, out_move,
-                              out_tours, plan.row_cache);
+        // (one sweep per launch: no symmetry verdict, so relocate could use the row cache for one of its two gathers only -- off)
+        if (int rc = plan_cluster(reinterpret_cast<const void *>(moves_cluster_kernel), csize, B, n, plain, "moves_cluster_kernel", &plan,
+                                  false)) return rc;
+        if (plan.csize > 1)
+            return launch_planned(moves_cluster_kernel, plan, st, op, o2a, D, stride, tours, pos, B, n, fi, out_delta, out_move,
+                                  out_tours, plan.row_cache);
     }
     if (stride == 0 && staged <= limit) {
         if (int rc = ensure_smem(moves_kernel<true>, staged)) return rc;
@@ -1351,8 +1360,9 @@ extern "C" int gnngls_local_search_batch(const double *D, int32_t *tours, double
         if (int rc = prepare_cluster_kernel(local_search_cluster_kernel)) return rc;
         if (int rc = plan_cluster(reinterpret_cast<const void *>(local_search_cluster_kernel), csize, B, n, plain,
                                   "local_search_cluster_kernel", &plan)) return rc;
-        return launch_planned(local_search_cluster_kernel, plan, st, D, tours, costs, B, n, first_improvement, events, n_events,
-                              max_events, status, reinterpret_cast<long long *>(counters), plan.row_cache);
+        if (plan.csize > 1)
+            return launch_planned(local_search_cluster_kernel, plan, st, D, tours, costs, B, n, first_improvement, events, n_events,
+                                  max_events, status, reinterpret_cast<long long *>(counters), plan.row_cache);
     }
     if (staged <= (size_t)gnngls::device_max_optin_smem()) {
         if (int rc = ensure_smem(local_search_kernel<true>, staged)) return rc;
@@ -1407,7 +1417,8 @@ extern "C" int gnngls_gls_batch(const gnngls_gls_args *args, void *stream) {
         if (int rc = plan_cluster(reinterpret_cast<const void *>(gls_cluster_kernel), csize, a.B, a.n, plain, "gls_cluster_kernel", &plan))
             return rc;
         P.row_cache = plan.row_cache;
-        return launch_planned(gls_cluster_kernel, plan, st, P);
+        if (plan.csize > 1) return launch_planned(gls_cluster_kernel, plan, st, P);
+        P.row_cache = 0;
     }
     if (fits && !use_global) {
         if (int rc = ensure_smem(gls_kernel<true>, staged)) return rc;
