@@ -518,17 +518,29 @@ __device__ __forceinline__ void apply_move(int op, int *t, int *tmp, int i, int 
     else apply_relocate(t, tmp, i, j);
 }
 
+// strictly sequential fp64 sum of E[0..n) (gnngls/__init__.py:17-21), one thread.  Loads are batched four at a time (they do not depend
+// on the running sum); the remainder loop is kept rolled so that ptxas does not predicate the uniform-register moves it likes to use for a
+// single-thread reduction (tests/test_abi_and_host.py::test_no_divergent_uniform_register_moves_in_sass).
+__device__ __forceinline__ double sequential_sum(const double *E, int n) {
+    double c = 0.0;
+    int p = 0;
+#pragma unroll 1
+    for (; p + 4 <= n; p += 4) {
+        const double e0 = E[p], e1 = E[p + 1], e2 = E[p + 2], e3 = E[p + 3];
+        c = __dadd_rn(c, e0); c = __dadd_rn(c, e1); c = __dadd_rn(c, e2); c = __dadd_rn(c, e3);
+    }
+#pragma unroll 1
+    for (; p < n; ++p) c = __dadd_rn(c, E[p]);
+    return c;
+}
+
 // gnngls/__init__.py:17-21: c = 0; c += w for consecutive edges (strictly sequential fp64 sum).
 // Edge weights are gathered in parallel into E, then thread 0 adds them in order.
 template <class M>
 __device__ double tour_cost_seq(const int *t, int n, const M &D, double *E, double *slot) {
     for (int p = threadIdx.x; p < n; p += blockDim.x) E[p] = D(t[p], t[p + 1]);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double c = 0.0;
-        for (int p = 0; p < n; ++p) c = __dadd_rn(c, E[p]);
-        *slot = c;
-    }
+    if (threadIdx.x == 0) *slot = sequential_sum(E, n);
     __syncthreads();
     return *slot;
 }
@@ -1101,11 +1113,7 @@ __global__ void __launch_bounds__(1024) nn_init_block_kernel(int guide_kind, con
             const double *Db = Dg + (size_t)b * nn;
             for (int p = threadIdx.x; p < n; p += blockDim.x) E[p] = Db[(size_t)tour[p] * n + tour[p + 1]];
             __syncthreads();
-            if (threadIdx.x == 0) {
-                double c = 0.0;
-                for (int p = 0; p < n; ++p) c = __dadd_rn(c, E[p]);
-                out_costs[b] = c;
-            }
+            if (threadIdx.x == 0) out_costs[b] = sequential_sum(E, n);
         }
         __syncthreads();
     }
