@@ -1141,6 +1141,7 @@ __global__ void tour_cost_kernel(const double *Dg, const int *tours, int B, int 
 // launch helpers
 // ----------------------------------------------------------------------------------------------
 int pick_threads(int n) {
+    if (const char *e = getenv("GNNGLS_SEARCH_THREADS")) { const int t = atoi(e); if (t >= 32 && t <= 1024 && t % 32 == 0) return t; }   // A/B knob
     if (n <= 40) return 64;
     if (n <= 72) return 128;
     if (n <= 160) return 256;
