@@ -1264,7 +1264,11 @@ int plan_cluster(const void *kernel, int limit, int B, int n, size_t base_smem, 
             if (limit < 0) break;                      // forced: that size, or the next smaller one that can be placed
         }
     }
-    GNNGLS_REQUIRE(plan->csize >= 2, GNNGLS_ERR_CUDA, "launch of %s failed: no cluster size could be placed", what);
+    if (plan->csize < 2) {                             // no cluster shape can be placed on this device: one CTA per instance
+        GNNGLS_REQUIRE(limit > 0, GNNGLS_ERR_CUDA, "launch of %s failed: the forced cluster size cannot be placed", what);
+        plan->csize = 1;
+        return GNNGLS_OK;
+    }
     // A cluster must bring clearly more threads to an instance than the one-CTA tier would (which runs every eligible batch in one
     // round): with the row cache's small CTAs and a batch that needs two rounds of clusters it does not (n = 1000 x 64: 2 x 416
     // against 1024 threads, measured slower) -- csize = 1 tells the caller to launch the one-CTA tier.

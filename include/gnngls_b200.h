@@ -57,8 +57,12 @@ const char *gnngls_last_error_string(void);
 /* ---------------------------------------------------------------------------------------------
  * Move evaluation — gnngls/operators.py:32-50 (two_opt_a2a), :129-147 (relocate_a2a),
  * :53-73 (two_opt_o2a), :106-126 (relocate_o2a).
- * One CTA per (instance); fp64 deltas in the reference's association order, no FMA; the winner
- * equals the reference's sequential first-strict-minimum scan.
+ * One CTA per instance -- or, when the batch is far below the SM count (B <= SMs, n >= 48), one
+ * thread-block cluster of up to 16 CTAs per instance whose members share the rows of the scan and
+ * exchange their winners through distributed shared memory (a2a sweeps, local_search, GLS and the
+ * nearest-neighbour constructor; results are bit-identical, the choice is made per launch;
+ * GNNGLS_CLUSTER=0 disables it).  fp64 deltas in the reference's association order, no FMA; the
+ * winner equals the reference's sequential first-strict-minimum scan.
  *   D            [B,n,n] fp64, or one [n,n] matrix shared by the batch when d_batch_stride == 0
  *   tours        [B,n+1] int32
  *   pos          [B] int32 (o2a only): the fixed index i, 0 < i < n
@@ -100,7 +104,8 @@ typedef struct gnngls_gls_args {
     int32_t *best_tours;        /* [B,n+1] out (in/out when resume)                               */
     double *best_costs;         /* [B]     out (in/out when resume)                               */
     double *k;                  /* [B] out when !resume (0.1*init_cost/n, :137), in when resume   */
-    int32_t *penalties;         /* [B,n,n] int32 in/out; may be NULL when !resume (not persisted) */
+    int32_t *penalties;         /* [B,n,n] int32 in/out; may be NULL when !resume (not persisted);
+                                   the L2-resident and cluster tiers need it                      */
     int32_t resume;             /* 0: zero penalties, run the initial local_search (:138-143)     */
     int32_t iter_begin;         /* index of the first outer iteration of this call                */
     int32_t n_iters;            /* number of outer iterations to run                              */

@@ -184,3 +184,32 @@ def test_no_divergent_uniform_register_moves_in_sass():
     # (R2UR.BROADCAST under an elect-style predicate, as in the tcgen05 GEMM kernels, is the legal form)
     bad = [l for l in sass.splitlines() if 'R2UR ' in l and '@' in l.split('R2UR')[0]]
     assert not bad, bad[:5]
+
+
+def test_cluster_tier_uses_cluster_barriers_and_distributed_shared_memory():
+    """The cluster tier of the search kernels must really be a thread-block-cluster program: cluster barriers,
+    generic stores through mapa-translated (distributed shared memory) addresses and cp.async staging in the SASS of
+    gls_cluster_kernel, and none of the cluster barriers in the one-CTA kernel."""
+    import shutil
+    import subprocess
+    from gnngls_b200 import build
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not available')
+    lib = build.build()
+    sass = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True, check=True).stdout
+    funcs = {}
+    name = None
+    for line in sass.splitlines():
+        if 'Function :' in line:
+            name = line.split('Function :')[1].strip()
+            funcs[name] = []
+        elif name is not None:
+            funcs[name].append(line)
+    def body(key, exclude=()):
+        hits = [k for k in funcs if key in k and not any(e in k for e in exclude)]
+        assert hits, key
+        return '\n'.join('\n'.join(funcs[k]) for k in hits)
+    cl = body('gls_cluster_kernel')
+    assert 'UCGABAR_ARV' in cl and 'UCGABAR_WAIT' in cl and 'LDGSTS' in cl and 'ST.E' in cl
+    solo = body('gls_kernel', exclude=('cluster',))
+    assert 'UCGABAR' not in solo
