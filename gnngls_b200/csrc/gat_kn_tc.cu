@@ -57,7 +57,20 @@ constexpr int X_KB = (XN / 8) * 128;                     // bytes of one 8-membe
 constexpr int X_BYTES = (KPAD / 8) * X_KB;               // 12 KB per team
 constexpr float kLeadGap = 6.f;                          // lead (log2 units) of the largest score above which its member is handled in fp32
 constexpr int TMEM_COLS = 128;                           // 64 columns indicator (K=128 as fp16 pairs) + 48 accumulator
-constexpr int MROW = 416;                                // floats per merge row in flight: two records (2 x 128 numerators, 2 x 16) + skip row (128)
+// Partial records.  The 16 numerators of a (row, head) travel as int16 with one shared power-of-two scale (KN_REC32 restores fp32):
+// a record shrinks from 576 to 320 bytes per node and star, so the records in flight between a star and its merge (two to three
+// rounds of the grid) are half as likely to be evicted from L2 to HBM, and the epilogue writes one 32-byte store per head instead
+// of two.  The scale costs no storage: a partial (v, den, M) -- numerators, denominator, reference exponent -- means the same as
+// (v c, den c, M - log2 c) for any c > 0, so the epilogue picks c = 2^-e (1 - 2^-15) with max|v| c in [2^14, 2^15), rounds v c to
+// integers and stores den c and M - log2 c in the fp32 part of the record; the merge is unchanged.  Absolute error <= 2^-15 of the
+// head's largest numerator (fp16 would give 2^-11 of every value: 4 x the kernel's whole error, measured).
+#ifdef KN_REC32
+constexpr bool REC16 = false;
+#else
+constexpr bool REC16 = true;
+#endif
+constexpr int RECV_BYTES = REC16 ? 2 * 128 * 2 : 2 * 128 * 4;   // both stars' numerators of one node
+constexpr int MROW = RECV_BYTES / 4 + 32 + 128;          // floats per merge row in flight: two records' numerators, 2 x 16 (denominator, max), skip row (128)
 constexpr int ESTR = 20;                                 // floats per member in the score buffer: el (8), er (8), pad (bank spread)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,6 +148,10 @@ __device__ __forceinline__ void st_keep8(float *p, float4 a, float4 b) {
     asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)),
                  "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)),
                  "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w)) : "memory");
+}
+__device__ __forceinline__ void st_keep8u(void *p, const uint32_t (&w)[8]) {
+    asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 __device__ __forceinline__ void ldg8(const void *p, uint4 &a, uint4 &b) {
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
@@ -326,9 +343,9 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 for (int q = 0; q < rows; ++q) {
                     const size_t node = mnode0 + r0 + 32 * q;
                     const uint32_t dst = smem_u32(MLAND + q * MROW);
-                    bulk_g2s(dst, a.recV + node * 2 * D_, 2 * D_ * 4, mb, pol_stream);
-                    bulk_g2s(dst + 2 * D_ * 4, a.recDM + node * 4 * H_, 4 * H_ * 4, mb, pol_stream);
-                    bulk_g2s(dst + 2 * D_ * 4 + 128, a.h + node * D_, D_ * 4, mb, pol_stream);
+                    bulk_g2s(dst, reinterpret_cast<const unsigned char *>(a.recV) + node * RECV_BYTES, RECV_BYTES, mb, pol_stream);
+                    bulk_g2s(dst + RECV_BYTES, a.recDM + node * 4 * H_, 4 * H_ * 4, mb, pol_stream);
+                    bulk_g2s(dst + RECV_BYTES + 128, a.h + node * D_, D_ * 4, mb, pol_stream);
                 }
             }
         };
@@ -387,9 +404,21 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 if (r >= mhi) break;
                 const size_t node = mnode0 + r;
                 const float *Lr = MLAND + q * MROW;
-                const float4 lv = *reinterpret_cast<const float4 *>(Lr + 4 * lane), uv = *reinterpret_cast<const float4 *>(Lr + D_ + 4 * lane);
-                const float2 l2 = *reinterpret_cast<const float2 *>(Lr + 2 * D_ + 2 * (lane >> 2)), u2 = *reinterpret_cast<const float2 *>(Lr + 2 * D_ + 16 + 2 * (lane >> 2));
-                const float4 hv = *reinterpret_cast<const float4 *>(Lr + 2 * D_ + 32 + 4 * lane);
+                float4 lv, uv;
+                if (REC16) {
+                    const uint2 lr = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(Lr) + 8 * lane);
+                    const uint2 ur = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(Lr) + 256 + 8 * lane);
+                    auto lo16 = [](uint32_t w) { return (float)((int)(w << 16) >> 16); };
+                    auto hi16 = [](uint32_t w) { return (float)((int)w >> 16); };
+                    lv = make_float4(lo16(lr.x), hi16(lr.x), lo16(lr.y), hi16(lr.y));
+                    uv = make_float4(lo16(ur.x), hi16(ur.x), lo16(ur.y), hi16(ur.y));
+                } else {
+                    lv = *reinterpret_cast<const float4 *>(Lr + 4 * lane);
+                    uv = *reinterpret_cast<const float4 *>(Lr + D_ + 4 * lane);
+                }
+                constexpr int RV = RECV_BYTES / 4;             // floats of landing buffer taken by the numerators
+                const float2 l2 = *reinterpret_cast<const float2 *>(Lr + RV + 2 * (lane >> 2)), u2 = *reinterpret_cast<const float2 *>(Lr + RV + 16 + 2 * (lane >> 2));
+                const float4 hv = *reinterpret_cast<const float4 *>(Lr + RV + 32 + 4 * lane);
                 const float mx = fmaxf(l2.y, u2.y);
                 const float s1 = ex2(l2.y - mx), s2 = ex2(u2.y - mx);
                 const float inv = rcp_approx(fmaf(l2.x, s1, u2.x * s2));
@@ -402,8 +431,8 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 st_hint4(reinterpret_cast<float4 *>(a.h1 + node * D_) + lane, o, pol_stream);
                 if (a.h1_tf32) st_hint4(reinterpret_cast<float4 *>(a.h1_tf32 + node * D_) + lane, tf32_round4(o), pol_stream);
                 // the consumed records are dead (read exactly once): drop their dirty L2 lines instead of writing them back
-                if (lane < 8) discard_l2_128(a.recV + node * 2 * D_ + 32 * lane);
-                else if (lane == 8) discard_l2_128(a.recDM + node * 4 * H_);
+                if (lane < RECV_BYTES / 128) discard_l2_128(reinterpret_cast<const unsigned char *>(a.recV) + node * RECV_BYTES + 128 * lane);
+                else if (lane == RECV_BYTES / 128) discard_l2_128(a.recDM + node * 4 * H_);
             }
             __syncwarp();
             if (hs + 1 < H_) fetch_merge_rows(hs + 1);
@@ -580,8 +609,30 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                         }
                         __syncwarp(__activemask());
                     }
-                    st_keep8(reinterpret_cast<float *>(rv), v[0], v[1]);
-                    st_keep8(reinterpret_cast<float *>(rv + 2), v[2], v[3]);
+                    if (REC16) {
+                        float mx = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[q].x), fabsf(v[q].y))), fmaxf(fabsf(v[q].z), fabsf(v[q].w)));
+                        int E = __float_as_int(mx) >> 23;                          // biased exponent of the largest numerator
+                        E = E < 40 ? 40 : (E > 230 ? 230 : E);                     // (keeps 2^-e and den 2^-e finite; |v| < 2^-87 rounds to 0)
+                        // c = 2^-e (1 - 2^-15), e = (E - 127) - 14: max|v| c < 32767.5, so the rounded value always fits an int16
+                        const float scale = __int_as_float((268 - E) << 23) * 0.999969482421875f;
+                        den *= scale;
+                        M += (float)(E - 141) + 4.4028e-5f;                        // M - log2(c)
+                        constexpr float kMagic = 12582912.f;                       // 1.5 * 2^23: the low mantissa bits of x + kMagic are rint(x)
+                        uint32_t w[8];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t b0 = __float_as_uint(fmaf(v[q].x, scale, kMagic)), b1 = __float_as_uint(fmaf(v[q].y, scale, kMagic));
+                            const uint32_t b2 = __float_as_uint(fmaf(v[q].z, scale, kMagic)), b3 = __float_as_uint(fmaf(v[q].w, scale, kMagic));
+                            w[2 * q] = __byte_perm(b0, b1, 0x5410);
+                            w[2 * q + 1] = __byte_perm(b2, b3, 0x5410);
+                        }
+                        st_keep8u(reinterpret_cast<unsigned char *>(a.recV) + ((my_node * 2 + sl) * D_ + head * F_) * 2, w);
+                    } else {
+                        st_keep8(reinterpret_cast<float *>(rv), v[0], v[1]);
+                        st_keep8(reinterpret_cast<float *>(rv + 2), v[2], v[3]);
+                    }
                     DMS[head * 128 + tt] = make_float2(den, M);            // written out with the other heads' at the end of the star
                 }
                 KN_STAMP(12);                                          // partial
@@ -626,7 +677,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
 namespace gnngls {
 size_t kn_tc_workspace_bytes(int B, int n) {
     const size_t M = (size_t)B * ((size_t)n * (n - 1) / 2);
-    return sizeof(float) * M * (2 * D_ + 4 * H_) + sizeof(int) * ((size_t)B + 4);   // two records per node, one counter per instance, slot + slice counters
+    return M * ((size_t)RECV_BYTES + sizeof(float) * 4 * H_) + sizeof(int) * ((size_t)B + 4);   // two records per node, one counter per instance, slot + slice counters
 }
 
 int launch_kn_tc(const KnArgs &args_in, int B, void *workspace, cudaStream_t st) {
@@ -637,7 +688,7 @@ int launch_kn_tc(const KnArgs &args_in, int B, void *workspace, cudaStream_t st)
     GNNGLS_REQUIRE(n <= KPAD, GNNGLS_ERR_UNSUPPORTED, "the tcgen05 K_n kernel handles n <= %d", KPAD);
     const size_t M = (size_t)B * ((size_t)n * (n - 1) / 2);
     args.recV = static_cast<float *>(workspace);
-    args.recDM = args.recV + M * 2 * D_;
+    args.recDM = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) + M * RECV_BYTES);
     args.flags = reinterpret_cast<int *>(args.recDM + M * 4 * H_);
     GNNGLS_CUDA_OK(cudaMemsetAsync(args.flags, 0, sizeof(int) * ((size_t)B + 4), st));
     auto kernel = pair ? gat_kn_tc_kernel<true> : gat_kn_tc_kernel<false>;

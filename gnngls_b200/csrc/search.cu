@@ -847,6 +847,9 @@ __device__ __forceinline__ void gls_body(const GlsDev &P) {
         if (a.resume) for (int p = threadIdx.x; p <= n; p += blockDim.x) s.best_tour[p] = a.best_tours[(size_t)b * (n + 1) + p];
         __syncthreads();
         if constexpr (CL) cluster_check_symmetric(Db, n, team, s.red);
+#ifdef GLS_STAMPS
+        if (threadIdx.x == 0 && b == inst0) { long long *sb = gls_stamp_buf(); for (int q = 0; q < 8; ++q) sb[q] = 0; sb[8] = clock64(); }
+#endif
         double k;
         if (a.resume) k = a.k[b];
         else k = __ddiv_rn(__dmul_rn(0.1, s.slot[0]), (double)n);                // :137
@@ -855,6 +858,7 @@ __device__ __forceinline__ void gls_body(const GlsDev &P) {
 
         if (!a.resume) {
             local_search_dev(s, n, D, fi, &s.slot[0], log, cnt, team);            // :142
+            if (b == inst0) GLS_STAMP(7);                                         // (one-CTA tier: everything of the local search)
             for (int p = threadIdx.x; p <= n; p += blockDim.x) s.best_tour[p] = s.tour[p];   // :143
             if (threadIdx.x == 0) s.slot[1] = s.slot[0];
             __syncthreads();
@@ -930,6 +934,7 @@ __device__ __forceinline__ void gls_body(const GlsDev &P) {
                 }
 #undef GLS_PERTURB
             }
+            if (b == inst0) GLS_STAMP(6);                                         // perturbation
             if constexpr (CL) {
                 // hand member 0's perturbed tour and its cost to the other members.  Member 0 changes neither before
                 // the first barrier of the local search below, which no member reaches before it has finished copying.
@@ -943,6 +948,7 @@ __device__ __forceinline__ void gls_body(const GlsDev &P) {
                 __syncthreads();
             }
             local_search_dev(s, n, D, fi, &s.slot[0], log, cnt, team);            // :188
+            if (b == inst0) GLS_STAMP(7);
             if (s.slot[0] < s.slot[1]) {                                          // :190-191 (block-uniform)
                 for (int p = threadIdx.x; p <= n; p += blockDim.x) s.best_tour[p] = s.tour[p];
                 __syncthreads();
@@ -951,6 +957,9 @@ __device__ __forceinline__ void gls_body(const GlsDev &P) {
             __syncthreads();
         }
 
+#ifdef GLS_STAMPS
+        if (threadIdx.x == 0 && b == inst0 && blockIdx.x < 16) for (int q = 0; q < 8; ++q) g_gls_stamps[blockIdx.x * 8 + q] = gls_stamp_buf()[q];
+#endif
         // ---- store state (member 0 of a cluster; every member holds the same tours and costs)
         if (lead) {
             for (int p = threadIdx.x; p <= n; p += blockDim.x) {
