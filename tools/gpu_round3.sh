@@ -23,4 +23,10 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:'gls
 for tool in memcheck racecheck; do
   GNNGLS_ROWCACHE=1 timeout 600 compute-sanitizer --tool $tool --print-limit 5 python tools/gls_diff.py 64 2 2 > $O/${T}_san_${tool}_cluster.log 2>&1; echo "$tool cluster rc=$?"
 done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $O/${T}_launches.csv \
+    $B --global-instances 512 --steps 1 --warmup 1 > $O/${T}_ncu_list.log 2>&1; echo "ncu list rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gat_kn_tc|ff_fused|gemm_tf32|gls_kernel' \
+    --launch-skip 12 --launch-count 7 -f -o $O/${T}_prof $B --global-instances 512 --steps 1 --warmup 1 > $O/${T}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gat_kn_tc -s 2 -c 1 -f -o $O/${T}_kn \
+    python tools/kn_bench.py 100 256 2 > $O/${T}_ncu_kn.log 2>&1; echo "ncu kn rc=$?"
 timeout 900 python tools/moves_sweep.py > $O/${T}_sweep.jsonl 2> $O/${T}_sweep.err; echo "sweep rc=$?"
