@@ -26,8 +26,7 @@ SOURCES = {
     'glue.cu': ['-fmad=false'],
     'gat.cu': [],
     'gat_kn.cu': [],
-    'gat_kn_tc.cu': (['-DKN_STAMPS'] if os.environ.get('GNNGLS_KN_STAMPS') else []) +   # phase timers (tools/kn_stamps.py)
-                    (['-DKN_REC32'] if os.environ.get('GNNGLS_KN_REC32') else []),     # fp32 partial records (A/B)
+    'gat_kn_tc.cu': ['-DKN_STAMPS'] if os.environ.get('GNNGLS_KN_STAMPS') else [],   # phase timers (tools/kn_stamps.py)
     'dense.cu': [],
     'model.cu': [],
 }

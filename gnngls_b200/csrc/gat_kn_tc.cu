@@ -57,20 +57,17 @@ constexpr int X_KB = (XN / 8) * 128;                     // bytes of one 8-membe
 constexpr int X_BYTES = (KPAD / 8) * X_KB;               // 12 KB per team
 constexpr float kLeadGap = 6.f;                          // lead (log2 units) of the largest score above which its member is handled in fp32
 constexpr int TMEM_COLS = 128;                           // 64 columns indicator (K=128 as fp16 pairs) + 48 accumulator
-// Partial records.  The 16 numerators of a (row, head) travel as int16 with one shared power-of-two scale (KN_REC32 restores fp32):
+// Partial records.  The 16 numerators of a (row, head) travel as int16 with one shared scale (round 2: fp32):
 // a record shrinks from 576 to 320 bytes per node and star, so the records in flight between a star and its merge (two to three
 // rounds of the grid) are half as likely to be evicted from L2 to HBM, and the epilogue writes one 32-byte store per head instead
 // of two.  The scale costs no storage: a partial (v, den, M) -- numerators, denominator, reference exponent -- means the same as
 // (v c, den c, M - log2 c) for any c > 0, so the epilogue picks c = 2^-e (1 - 2^-15) with max|v| c in [2^14, 2^15), rounds v c to
 // integers and stores den c and M - log2 c in the fp32 part of the record; the merge is unchanged.  Absolute error <= 2^-15 of the
 // head's largest numerator (fp16 would give 2^-11 of every value: 4 x the kernel's whole error, measured).
-#ifdef KN_REC32
-constexpr bool REC16 = false;
-#else
-constexpr bool REC16 = true;
-#endif
-constexpr int RECV_BYTES = REC16 ? 2 * 128 * 2 : 2 * 128 * 4;   // both stars' numerators of one node
-constexpr int MROW = RECV_BYTES / 4 + 32 + 128;          // floats per merge row in flight: two records' numerators, 2 x 16 (denominator, max), skip row (128)
+// One record per node holds BOTH stars' partials, so that the merge fetches it (and the next node's) with one bulk copy:
+//   [slot 0: 128 int16][slot 1: 128 int16][slot 0: 8 x (den, exponent) fp32][slot 1: 8 x (den, exponent) fp32]  = 640 bytes
+constexpr int REC_BYTES = 2 * 256 + 2 * 64;
+constexpr int MROW = (REC_BYTES + 512) / 4;              // floats per merge row in flight: the node's record + its skip row (128 fp32)
 constexpr int ESTR = 20;                                 // floats per member in the score buffer: el (8), er (8), pad (bank spread)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -332,21 +329,19 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h + (mnode0 + mlo) * D_ + 32 * idx));
         }
         if (nxt < slots) issue_scores(nxt, cbuf ^ 1);
-        // merge rows of MMA shadow `hs` (this warp: rows mlo + 4 hs + warp, + 32): records of both stars and skip row -> shared memory
+        // merge rows of MMA shadow `hs` (this warp: the two CONSECUTIVE rows mlo + 8 hs + 2 warp, + 1): their records are adjacent in
+        // memory and so are their skip rows -- two bulk copies per warp and shadow land [record, record, skip, skip] in shared memory
         auto fetch_merge_rows = [&](int hs) {
-            const int r0 = mlo + hs * T_WARPS + warp;
+            const int r0 = mlo + hs * 2 * T_WARPS + 2 * warp;
             if (lane == 0 && r0 < mhi) {
-                const int rows = (r0 + 32 < mhi) ? 2 : 1;
+                const uint32_t rows = (r0 + 1 < mhi) ? 2u : 1u;
                 const uint32_t mb = smem_u32(mbar);
                 asm volatile("fence.proxy.async.global;" ::: "memory");    // the records were made visible to the generic proxy
-                mbar_arrive_expect_tx(mb, rows * MROW * 4);
-                for (int q = 0; q < rows; ++q) {
-                    const size_t node = mnode0 + r0 + 32 * q;
-                    const uint32_t dst = smem_u32(MLAND + q * MROW);
-                    bulk_g2s(dst, reinterpret_cast<const unsigned char *>(a.recV) + node * RECV_BYTES, RECV_BYTES, mb, pol_stream);
-                    bulk_g2s(dst + RECV_BYTES, a.recDM + node * 4 * H_, 4 * H_ * 4, mb, pol_stream);
-                    bulk_g2s(dst + RECV_BYTES + 128, a.h + node * D_, D_ * 4, mb, pol_stream);
-                }
+                mbar_arrive_expect_tx(mb, rows * (REC_BYTES + 512));
+                const size_t node = mnode0 + r0;
+                const uint32_t dst = smem_u32(MLAND);
+                bulk_g2s(dst, reinterpret_cast<const unsigned char *>(a.recV) + node * REC_BYTES, rows * REC_BYTES, mb, pol_stream);
+                bulk_g2s(dst + 2 * REC_BYTES, a.h + node * D_, rows * 512, mb, pol_stream);
             }
         };
         cp_async_commit();
@@ -393,32 +388,24 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         // the merge rows fetched one shadow ago: combine the two stars' records in fixed (lower, higher) order, apply bias + skip +
         // BN1, write h1; then fetch the rows of the next shadow
         auto merge_rows = [&](int hs) {
-            if (mlo + hs * T_WARPS + warp < mhi) {                     // (warp-uniform) rows were requested for this shadow
+            if (mlo + hs * 2 * T_WARPS + 2 * warp < mhi) {             // (warp-uniform) rows were requested for this shadow
                 mbar_wait(mbar, mparity);
                 mparity ^= 1;
             }
             KN_STAMP(15);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const int r = mlo + hs * T_WARPS + warp + 32 * q;
+                const int r = mlo + hs * 2 * T_WARPS + 2 * warp + q;
                 if (r >= mhi) break;
                 const size_t node = mnode0 + r;
-                const float *Lr = MLAND + q * MROW;
-                float4 lv, uv;
-                if (REC16) {
-                    const uint2 lr = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(Lr) + 8 * lane);
-                    const uint2 ur = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(Lr) + 256 + 8 * lane);
-                    auto lo16 = [](uint32_t w) { return (float)((int)(w << 16) >> 16); };
-                    auto hi16 = [](uint32_t w) { return (float)((int)w >> 16); };
-                    lv = make_float4(lo16(lr.x), hi16(lr.x), lo16(lr.y), hi16(lr.y));
-                    uv = make_float4(lo16(ur.x), hi16(ur.x), lo16(ur.y), hi16(ur.y));
-                } else {
-                    lv = *reinterpret_cast<const float4 *>(Lr + 4 * lane);
-                    uv = *reinterpret_cast<const float4 *>(Lr + D_ + 4 * lane);
-                }
-                constexpr int RV = RECV_BYTES / 4;             // floats of landing buffer taken by the numerators
-                const float2 l2 = *reinterpret_cast<const float2 *>(Lr + RV + 2 * (lane >> 2)), u2 = *reinterpret_cast<const float2 *>(Lr + RV + 16 + 2 * (lane >> 2));
-                const float4 hv = *reinterpret_cast<const float4 *>(Lr + RV + 32 + 4 * lane);
+                const unsigned char *Lr = reinterpret_cast<const unsigned char *>(MLAND) + q * REC_BYTES;
+                const uint2 lr = *reinterpret_cast<const uint2 *>(Lr + 8 * lane), ur = *reinterpret_cast<const uint2 *>(Lr + 256 + 8 * lane);
+                auto lo16 = [](uint32_t w) { return (float)((int)(w << 16) >> 16); };
+                auto hi16 = [](uint32_t w) { return (float)((int)w >> 16); };
+                const float4 lv = make_float4(lo16(lr.x), hi16(lr.x), lo16(lr.y), hi16(lr.y));
+                const float4 uv = make_float4(lo16(ur.x), hi16(ur.x), lo16(ur.y), hi16(ur.y));
+                const float2 l2 = *reinterpret_cast<const float2 *>(Lr + 512 + 8 * (lane >> 2)), u2 = *reinterpret_cast<const float2 *>(Lr + 576 + 8 * (lane >> 2));
+                const float4 hv = *reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(MLAND) + 2 * REC_BYTES + q * 512 + 16 * lane);
                 const float mx = fmaxf(l2.y, u2.y);
                 const float s1 = ex2(l2.y - mx), s2 = ex2(u2.y - mx);
                 const float inv = rcp_approx(fmaf(l2.x, s1, u2.x * s2));
@@ -431,8 +418,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 st_hint4(reinterpret_cast<float4 *>(a.h1 + node * D_) + lane, o, pol_stream);
                 if (a.h1_tf32) st_hint4(reinterpret_cast<float4 *>(a.h1_tf32 + node * D_) + lane, tf32_round4(o), pol_stream);
                 // the consumed records are dead (read exactly once): drop their dirty L2 lines instead of writing them back
-                if (lane < RECV_BYTES / 128) discard_l2_128(reinterpret_cast<const unsigned char *>(a.recV) + node * RECV_BYTES + 128 * lane);
-                else if (lane == RECV_BYTES / 128) discard_l2_128(a.recDM + node * 4 * H_);
+                if (lane < REC_BYTES / 128) discard_l2_128(reinterpret_cast<const unsigned char *>(a.recV) + node * REC_BYTES + 128 * lane);
             }
             __syncwarp();
             if (hs + 1 < H_) fetch_merge_rows(hs + 1);
@@ -584,7 +570,6 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                     const float k1 = C1 * scl, k2 = C2 * scl, ks = (self_a ? C1 : C2) * scl;
                     const unsigned char *xself = xrow + (self_a ? 0 : 256);        // this member's own products in the branch it was counted in
                     const int sl = i < lt ? 0 : 1;                     // slot 0: written by the star of the lower vertex
-                    float4 *rv = reinterpret_cast<float4 *>(a.recV + (my_node * 2 + sl) * D_ + head * F_);
                     const float *TOTl = TOTs + 20 + (head & 1) * 16;
                     const uint4 xq0 = *reinterpret_cast<const uint4 *>(xself), xq1 = *reinterpret_cast<const uint4 *>(xself + 128);
                     const uint32_t xsw[8] = {xq0.x, xq0.y, xq0.z, xq0.w, xq1.x, xq1.y, xq1.z, xq1.w};
@@ -609,7 +594,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                         }
                         __syncwarp(__activemask());
                     }
-                    if (REC16) {
+                    {
                         float mx = 0.f;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[q].x), fabsf(v[q].y))), fmaxf(fabsf(v[q].z), fabsf(v[q].w)));
@@ -628,10 +613,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                             w[2 * q] = __byte_perm(b0, b1, 0x5410);
                             w[2 * q + 1] = __byte_perm(b2, b3, 0x5410);
                         }
-                        st_keep8u(reinterpret_cast<unsigned char *>(a.recV) + ((my_node * 2 + sl) * D_ + head * F_) * 2, w);
-                    } else {
-                        st_keep8(reinterpret_cast<float *>(rv), v[0], v[1]);
-                        st_keep8(reinterpret_cast<float *>(rv + 2), v[2], v[3]);
+                        st_keep8u(reinterpret_cast<unsigned char *>(a.recV) + my_node * REC_BYTES + sl * 256 + head * 32, w);
                     }
                     DMS[head * 128 + tt] = make_float2(den, M);            // written out with the other heads' at the end of the star
                 }
@@ -642,7 +624,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         if (live) {                                                    // this row's 8 x (denominator, max): one 64-byte chunk of the record
             const float2 d0 = DMS[tt], d1 = DMS[128 + tt], d2 = DMS[256 + tt], d3 = DMS[384 + tt];
             const float2 d4 = DMS[512 + tt], d5 = DMS[640 + tt], d6 = DMS[768 + tt], d7 = DMS[896 + tt];
-            float *rd = a.recDM + (my_node * 2 + (i < lt ? 0 : 1)) * 2 * H_;
+            float *rd = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(a.recV) + my_node * REC_BYTES + 512 + (i < lt ? 0 : 64));
             st_keep8(rd, make_float4(d0.x, d0.y, d1.x, d1.y), make_float4(d2.x, d2.y, d3.x, d3.y));
             st_keep8(rd + 8, make_float4(d4.x, d4.y, d5.x, d5.y), make_float4(d6.x, d6.y, d7.x, d7.y));
         }
@@ -677,7 +659,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
 namespace gnngls {
 size_t kn_tc_workspace_bytes(int B, int n) {
     const size_t M = (size_t)B * ((size_t)n * (n - 1) / 2);
-    return M * ((size_t)RECV_BYTES + sizeof(float) * 4 * H_) + sizeof(int) * ((size_t)B + 4);   // two records per node, one counter per instance, slot + slice counters
+    return M * (size_t)REC_BYTES + sizeof(int) * ((size_t)B + 4);   // one record (both stars) per node, one counter per instance, slot + slice counters
 }
 
 int launch_kn_tc(const KnArgs &args_in, int B, void *workspace, cudaStream_t st) {
@@ -688,8 +670,8 @@ int launch_kn_tc(const KnArgs &args_in, int B, void *workspace, cudaStream_t st)
     GNNGLS_REQUIRE(n <= KPAD, GNNGLS_ERR_UNSUPPORTED, "the tcgen05 K_n kernel handles n <= %d", KPAD);
     const size_t M = (size_t)B * ((size_t)n * (n - 1) / 2);
     args.recV = static_cast<float *>(workspace);
-    args.recDM = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) + M * RECV_BYTES);
-    args.flags = reinterpret_cast<int *>(args.recDM + M * 4 * H_);
+    args.recDM = nullptr;
+    args.flags = reinterpret_cast<int *>(static_cast<unsigned char *>(workspace) + M * REC_BYTES);
     GNNGLS_CUDA_OK(cudaMemsetAsync(args.flags, 0, sizeof(int) * ((size_t)B + 4), st));
     auto kernel = pair ? gat_kn_tc_kernel<true> : gat_kn_tc_kernel<false>;
     GNNGLS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
