@@ -641,7 +641,8 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
         cur = nxt;
         nxt = SI[0];
         cand = SI[1];
-        __syncthreads();                                               // (SI is rewritten in the next iteration)
+        // (no barrier here: SI[0] and SI[1] are only rewritten at the end of the next iteration, many barriers from now; the top of the
+        //  iteration writes SI[2] alone)
         KN_STAMP(13);                                                  // end of star: barriers, publish
     }
 #ifdef KN_STAMPS

@@ -1153,7 +1153,8 @@ int pick_threads(int n) {
     if (const char *e = getenv("GNNGLS_SEARCH_THREADS")) { const int t = atoi(e); if (t >= 32 && t <= 1024 && t % 32 == 0) return t; }   // A/B knob
     if (n <= 40) return 64;
     if (n <= 72) return 128;
-    if (n <= 160) return 256;
+    if (n <= 160) return 192;      // TSP100: 7 CTAs of 6 warps per SM; same-box A/B of the GLS stage: 128 / 192 / 256 / 384 threads = 63.8 / 59.3 / 63.0 / 67.9 ms
+
     if (n <= 400) return 512;
     return 1024;
 }
