@@ -410,11 +410,16 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                 const float s1 = ex2(l2.y - mx), s2 = ex2(u2.y - mx);
                 const float inv = rcp_approx(fmaf(l2.x, s1, u2.x * s2));
                 const float a1 = s1 * inv, a2 = s2 * inv;
-                float4 o;
-                o.x = (hv.x + (fmaf(lv.x, a1, uv.x * a2) + bb4.x)) * sc4.x + sh4.x;
-                o.y = (hv.y + (fmaf(lv.y, a1, uv.y * a2) + bb4.y)) * sc4.y + sh4.y;
-                o.z = (hv.z + (fmaf(lv.z, a1, uv.z * a2) + bb4.z)) * sc4.z + sh4.z;
-                o.w = (hv.w + (fmaf(lv.w, a1, uv.w * a2) + bb4.w)) * sc4.w + sh4.w;
+                // (packed fp32 pairs; same operations and order as  (h + ((l a1 + u a2) + bias)) scale + shift -- the product-sum of the last
+                //  step is a fused multiply-add exactly as nvcc contracts the scalar expression)
+                const float2 a1p = make_float2(a1, a1), a2p = make_float2(a2, a2);
+                const float2 g01 = __ffma2_rn(make_float2(lv.x, lv.y), a1p, __fmul2_rn(make_float2(uv.x, uv.y), a2p));
+                const float2 g23 = __ffma2_rn(make_float2(lv.z, lv.w), a1p, __fmul2_rn(make_float2(uv.z, uv.w), a2p));
+                const float2 y01 = __fadd2_rn(make_float2(hv.x, hv.y), __fadd2_rn(g01, make_float2(bb4.x, bb4.y)));
+                const float2 y23 = __fadd2_rn(make_float2(hv.z, hv.w), __fadd2_rn(g23, make_float2(bb4.z, bb4.w)));
+                const float2 o01 = __ffma2_rn(y01, make_float2(sc4.x, sc4.y), make_float2(sh4.x, sh4.y));
+                const float2 o23 = __ffma2_rn(y23, make_float2(sc4.z, sc4.w), make_float2(sh4.z, sh4.w));
+                const float4 o = make_float4(o01.x, o01.y, o23.x, o23.y);
                 st_hint4(reinterpret_cast<float4 *>(a.h1 + node * D_) + lane, o, pol_stream);
                 if (a.h1_tf32) st_hint4(reinterpret_cast<float4 *>(a.h1_tf32 + node * D_) + lane, tf32_round4(o), pol_stream);
                 // the consumed records are dead (read exactly once): drop their dirty L2 lines instead of writing them back
@@ -579,10 +584,16 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                         const float4 t4 = *reinterpret_cast<const float4 *>(TOTs + 4 * q);
                         const uint32_t xs0 = xsw[2 * q], xs1 = xsw[2 * q + 1];
                         const float2 x01 = __half22float2(*reinterpret_cast<const __half2 *>(&xs0)), x23 = __half22float2(*reinterpret_cast<const __half2 *>(&xs1));
-                        v[q].x = fmaf(k1, __uint_as_float(SA[4 * q]), fmaf(-k2, __uint_as_float(SB[4 * q]), fmaf(-ks, x01.x, k2 * t4.x)));
-                        v[q].y = fmaf(k1, __uint_as_float(SA[4 * q + 1]), fmaf(-k2, __uint_as_float(SB[4 * q + 1]), fmaf(-ks, x01.y, k2 * t4.y)));
-                        v[q].z = fmaf(k1, __uint_as_float(SA[4 * q + 2]), fmaf(-k2, __uint_as_float(SB[4 * q + 2]), fmaf(-ks, x23.x, k2 * t4.z)));
-                        v[q].w = fmaf(k1, __uint_as_float(SA[4 * q + 3]), fmaf(-k2, __uint_as_float(SB[4 * q + 3]), fmaf(-ks, x23.y, k2 * t4.w)));
+                        // packed fp32 pairs (FFMA2: two fmas per issue slot -- the kernel is issue-bound, not FMA-bound); same operations,
+                        // same order, same rounding as the scalar form  k1 SA + (-k2 SB + (-ks x + k2 t))
+                        const float2 k1p = make_float2(k1, k1), nk2p = make_float2(-k2, -k2), nksp = make_float2(-ks, -ks), k2p = make_float2(k2, k2);
+                        const float2 sa01 = make_float2(__uint_as_float(SA[4 * q]), __uint_as_float(SA[4 * q + 1]));
+                        const float2 sa23 = make_float2(__uint_as_float(SA[4 * q + 2]), __uint_as_float(SA[4 * q + 3]));
+                        const float2 sb01 = make_float2(__uint_as_float(SB[4 * q]), __uint_as_float(SB[4 * q + 1]));
+                        const float2 sb23 = make_float2(__uint_as_float(SB[4 * q + 2]), __uint_as_float(SB[4 * q + 3]));
+                        const float2 r01 = __ffma2_rn(k1p, sa01, __ffma2_rn(nk2p, sb01, __ffma2_rn(nksp, x01, __fmul2_rn(k2p, make_float2(t4.x, t4.y)))));
+                        const float2 r23 = __ffma2_rn(k1p, sa23, __ffma2_rn(nk2p, sb23, __ffma2_rn(nksp, x23, __fmul2_rn(k2p, make_float2(t4.z, t4.w)))));
+                        v[q] = make_float4(r01.x, r01.y, r23.x, r23.y);
                     }
                     if (fix) {                                         // (rare; a branch, not predicated instructions)
                         if (addlead) {
@@ -608,10 +619,10 @@ __global__ void __launch_bounds__(T_THREADS, 4) gat_kn_tc_kernel(const KnArgs a,
                         uint32_t w[8];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const uint32_t b0 = __float_as_uint(fmaf(v[q].x, scale, kMagic)), b1 = __float_as_uint(fmaf(v[q].y, scale, kMagic));
-                            const uint32_t b2 = __float_as_uint(fmaf(v[q].z, scale, kMagic)), b3 = __float_as_uint(fmaf(v[q].w, scale, kMagic));
-                            w[2 * q] = __byte_perm(b0, b1, 0x5410);
-                            w[2 * q + 1] = __byte_perm(b2, b3, 0x5410);
+                            const float2 scp = make_float2(scale, scale), mgp = make_float2(kMagic, kMagic);
+                            const float2 m01 = __ffma2_rn(make_float2(v[q].x, v[q].y), scp, mgp), m23 = __ffma2_rn(make_float2(v[q].z, v[q].w), scp, mgp);
+                            w[2 * q] = __byte_perm(__float_as_uint(m01.x), __float_as_uint(m01.y), 0x5410);
+                            w[2 * q + 1] = __byte_perm(__float_as_uint(m23.x), __float_as_uint(m23.y), 0x5410);
                         }
                         st_keep8u(reinterpret_cast<unsigned char *>(a.recV) + my_node * REC_BYTES + sl * 256 + head * 32, w);
                     }
