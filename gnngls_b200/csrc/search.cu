@@ -1255,7 +1255,7 @@ int plan_cluster(const void *kernel, int limit, int B, int n, size_t base_smem, 
         options[3] = Option{warps >= 8 ? 32 * (warps / 2) : 0, 1};
         if (getenv("GNNGLS_ROWCACHE")) options[0].threads = options[1].threads = 0;     // forced on: only the row-cache shapes
     }
-    double best_score = 0.0;
+    double best_score = 0.0, best_gain = 1.0;
     for (const Option &o : options) {
         if (!o.threads) continue;
         const size_t smem = base_smem + (o.rows ? (size_t)(o.threads / 32) * row_bytes : 0);
@@ -1263,13 +1263,16 @@ int plan_cluster(const void *kernel, int limit, int B, int n, size_t base_smem, 
             const int mc = max_active_clusters(kernel, c, o.threads, smem);
             if (mc < 1) continue;
             const int rounds = (B + mc - 1) / mc;
-            // a thread with the row cache gets ~1.35 x the work done (n = 500: 864 threads 7.0 ms, 1024 threads without 8.1 ms)
-            const double score = (double)rounds / ((double)c * o.threads * (o.rows ? 1.35 : 1.0));
+            // what a thread with the row cache gets done against one without grows with the row length (n = 500: 864 threads 7.0 ms
+            // against 1024 threads 8.1 ms = 1.4 x per thread; n = 1000: 416 threads 35 ms against 1024 threads 52 ms = 3.6 x)
+            const double gain = o.rows ? (n > 300 ? n / 300.0 : 1.0) : 1.0;
+            const double score = (double)rounds / ((double)c * o.threads * gain);
             // ties go to the smaller CTA: two of them share an SM's L1 and registers more evenly than one large one
             if (!plan->csize || score <= best_score) {
                 plan->csize = c; plan->threads = o.threads; plan->clusters = B < mc ? B : mc; plan->smem = smem;
                 plan->row_cache = o.rows;
                 best_score = score;
+                best_gain = gain;
             }
             if (limit < 0) break;                      // forced: that size, or the next smaller one that can be placed
         }
@@ -1282,7 +1285,7 @@ int plan_cluster(const void *kernel, int limit, int B, int n, size_t base_smem, 
     // A cluster must bring clearly more threads to an instance than the one-CTA tier would (which runs every eligible batch in one
     // round): with the row cache's small CTAs and a batch that needs two rounds of clusters it does not (n = 1000 x 64: 2 x 416
     // against 1024 threads, measured slower) -- csize = 1 tells the caller to launch the one-CTA tier.
-    if (limit > 0 && 2LL * plan->csize * plan->threads * plan->clusters < 3LL * pick_threads(n) * B) plan->csize = 1;
+    if (limit > 0 && 2.0 * plan->csize * plan->threads * plan->clusters * best_gain < 3.0 * pick_threads(n) * B) plan->csize = 1;
     return GNNGLS_OK;
 }
 
