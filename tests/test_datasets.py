@@ -63,3 +63,22 @@ def test_cli_writes_reference_style_run(tmp_path, batched):
         G = datasets.load_instance(data / name)
         lengths = sum(G.edges[e]['weight'] for e in G.edges if G.edges[e]['in_solution'])
         assert final[name] <= 2.5 * lengths and final[name] > 0
+    if batched:
+        # the guide must really steer the search: recompute the regrets the CLI used (same checkpoint, same kernels: bitwise
+        # reproducible), run the CPU oracle's nearest_neighbor + guided_local_search on them (test.py:79-95) and require the CLI's
+        # best costs to be the oracle's, bit for bit
+        import json
+        import gnngls_b200 as gnngls
+        from gnngls_b200 import models, pipeline
+        from oracle import gls_port
+        params = json.load(open(ckpt.parent / 'params.json'))
+        test_set = datasets.TSPDataset(data / 'test.txt')
+        model = models.EdgePropertyPredictionModel(1, params['embed_dim'], 1, params['n_layers'], n_heads=params['n_heads']).cuda()
+        model.load_state_dict(torch.load(ckpt, map_location='cuda')['model_state_dict'])
+        model.eval()
+        D = np.stack([gnngls.edge_matrix(datasets.load_instance(data / name), 'weight') for name in test_set.instances])
+        solver = pipeline.RegretGLS(model, pipeline.Scalers.from_sklearn(test_set.scalers))
+        regret = solver.predict_regret(torch.from_numpy(D).cuda()).cpu().numpy()
+        _, o_costs = gls_port.pipeline_batch(D, regret, 3, 5)[:2]
+        for b, name in enumerate(test_set.instances):
+            assert np.float64(final[name]).tobytes() == np.float64(o_costs[b]).tobytes(), (name, final[name], o_costs[b])
