@@ -213,3 +213,34 @@ def test_cluster_tier_uses_cluster_barriers_and_distributed_shared_memory():
     assert 'UCGABAR_ARV' in cl and 'UCGABAR_WAIT' in cl and 'LDGSTS' in cl and 'ST.E' in cl
     solo = body('gls_kernel', exclude=('cluster',))
     assert 'UCGABAR' not in solo
+
+
+def test_int16_record_scale_arithmetic():
+    """The K_n kernel's partial records (csrc/gat_kn_tc.cu): (v, den, M) == (v c, den c, M - log2 c) for any c > 0, and the c the
+    epilogue derives from the exponent of max|v| puts every rounded numerator inside int16 with 15 significant bits.  Restated in
+    numpy fp32 with the kernel's constants; the merge formula must give the same result from the scaled record (up to the int16
+    quantum) as from the unscaled one."""
+    rng = np.random.default_rng(0)
+    f32 = np.float32
+    for trial in range(2000):
+        mag = f32(2.0) ** f32(rng.integers(-20, 24))
+        v = (rng.standard_normal(16).astype(f32) * mag).astype(f32)
+        den, M = f32(rng.uniform(0.5, 99.0)), f32(rng.uniform(-30.0, 30.0))
+        mx = np.abs(v).max()
+        E = int(np.clip(int(np.array(mx, dtype=f32).view(np.int32)) >> 23, 40, 230))
+        scale = f32(np.array((268 - E) << 23, dtype=np.int32).view(f32) * f32(0.999969482421875))
+        q = np.rint(v.astype(np.float64) * np.float64(scale))                     # fma(v, c, 1.5 * 2^23) keeps rint(v c) in its low bits
+        assert np.abs(q).max() <= 32767 and (mx == 0 or np.abs(q).max() >= 16383), (mx, scale)
+        den_s, M_s = f32(den * scale), f32(M + f32(E - 141) + f32(4.4028e-5))
+        # merge with a second, unscaled partial (algorithms of merge_rows): out = (v1 s1 + v2 s2) / (den1 s1 + den2 s2), s = 2^(M - max M)
+        v2 = (rng.standard_normal(16) * float(mag)).astype(np.float64)
+        den2, M2 = rng.uniform(0.5, 99.0), float(M) + rng.uniform(-3.0, 3.0)
+
+        def merge(va, da, Ma):
+            mxm = max(Ma, M2)
+            s1, s2 = 2.0 ** (Ma - mxm), 2.0 ** (M2 - mxm)
+            return (va * s1 + v2 * s2) / (da * s1 + den2 * s2)
+        ref = merge(v.astype(np.float64), float(den), float(M))
+        got = merge(q, float(den_s), float(M_s))
+        tol = 2.0 ** -15 * float(mx) / float(den) * 1.5 + 1e-6 * np.abs(ref).max()    # half an int16 quantum of the head's largest numerator
+        assert np.abs(got - ref).max() <= tol + 1e-30, (trial, np.abs(got - ref).max(), tol)
